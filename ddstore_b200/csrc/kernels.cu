@@ -1,0 +1,687 @@
+// ddstore_b200/csrc/kernels.cu -- the get() hot path as hand-written sm_100a CUDA.
+//
+// What the reference does per sample (include/ddstore.hpp:197-238 + src/ddstore.cxx:5-17):
+//   owner = sortedsearch(lenlist, start); offset = lenlist[owner-1] (or 0); two range checks;
+//   MPI_Get of count*disp*itemsize bytes from the owner's window at row (start-offset).
+// What this file does per BATCH, in one persistent kernel:
+//   the same lookup + checks for every request, then a gather of all payloads from the owners'
+//   HBM shards (local, or peer-mapped over NVLink/NVSwitch via CUDA IPC) packed back to back into
+//   one contiguous device buffer.
+//
+// Kernel design (bandwidth-bound byte mover, no tensor cores):
+//   * The packed destination byte range [0, T) is cut into segments that warps claim dynamically
+//     (one atomic per segment), so load balance is by BYTES, not by request count (lengths differ
+//     100x in the variable-length configs) and not by owner (remote rows are slower than local).
+//   * Every warp is an autonomous pipeline with a private ring of S shared-memory stages.
+//     Lane 0 issues one 1-D TMA bulk load (cp.async.bulk global->shared, mbarrier complete_tx)
+//     per chunk of <= CH payload bytes, S-1 chunks ahead. Loads are issued on the 16-byte-aligned
+//     superset of the source range, so arbitrary element alignment (4-byte floats, single bytes)
+//     is legal for TMA.
+//   * Drain, by destination alignment relative to the staged bytes:
+//       - same 16-byte phase  -> lane 0 issues one TMA bulk store shared->global for the body;
+//       - different phase     -> all lanes read two aligned 16-byte vectors from shared memory,
+//                                funnel-shift them into place and issue aligned 128-bit stores;
+//       - <16-byte head/tail  -> single byte stores by the first lanes.
+//   * Request offsets in the packed buffer are an exclusive prefix sum of request sizes: arithmetic
+//     in the fixed-count entry; a block/warp-shuffle scan in the plan kernels for variable counts.
+//
+// Nothing here calls a library kernel; everything is launched from the ddsk_* functions at the end.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                                \
+            return (int)e__ ? (int)e__ : -1;                                                             \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a): mbarrier, 1-D TMA bulk copies, shared-memory vector access
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void stg128(void *p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// owner lookup + range checks, exactly the reference's arithmetic
+// ------------------------------------------------------------------------------------------------
+// src/ddstore.cxx:5-17: first i>=1 with vec[i-1] <= num < vec[i]; else 0 (also when out of range).
+__device__ __forceinline__ int dev_sortedsearch(const ddsk_var_t &v, int64_t num) {
+    int rtn = 0;
+    for (int i = 1; i < v.nranks; i++) {
+        if (v.lenlist[i - 1] <= num && num < v.lenlist[i]) {
+            rtn = i;
+            break;
+        }
+    }
+    return rtn;
+}
+
+// include/ddstore.hpp:205-214. Returns 0 or DDSK_CODE_*; *src = address of the first payload byte.
+__device__ __forceinline__ int dev_locate(const ddsk_var_t &v, int64_t start, int64_t count, uint64_t *src) {
+    int t = dev_sortedsearch(v, start);
+    int64_t off = t > 0 ? v.lenlist[t - 1] : 0;
+    if (start < off) return DDSK_CODE_START;
+    if (count < 0 || start + count > v.lenlist[t]) return DDSK_CODE_COUNT; /* count<0 is UB in the reference */
+    *src = (uint64_t)v.bases[t] + (uint64_t)(start - off) * (uint64_t)v.row_bytes; /* ddstore.hpp:229-236 */
+    return 0;
+}
+
+__device__ __forceinline__ void report(unsigned long long *status, int64_t req, int code) {
+    atomicMin(status, ((unsigned long long)req << 8) | (unsigned long long)code);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather kernel
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    ddsk_var_t var;
+    const int64_t *starts;   // FIXED: start row per request
+    int64_t count;           // FIXED: rows per request
+    const uint64_t *req_src; // VAR: planned source address (0 = skip)
+    const int64_t *req_dst;  // VAR: [nreq+1] exclusive scan; req_dst[nreq] = total bytes
+    int64_t nreq;
+    char *dst;
+    int64_t dst_cap;
+    int64_t *offsets_out; // FIXED: optional [nreq+1]
+    unsigned long long *status;
+    unsigned int *counters;
+};
+
+struct Chunk {
+    uint64_t src;
+    int64_t dpos; // byte position in the packed buffer
+    uint32_t n;
+};
+
+template <bool FIXED, int CH>
+struct ChunkWalker {
+    // warp-uniform state
+    int64_t seg_pos = 0, seg_end = 0, T = 0, seg_bytes = 0, nseg = 0, nb = 0;
+    int64_t r = 0, win_base = -64;
+    // per-lane window of 32 request descriptors
+    uint64_t w_src = 0;
+    int64_t w_dst = 0, w_n = 0;
+
+    __device__ __forceinline__ void load_window(const GatherArgs &a, int lane) {
+        win_base = r;
+        int64_t idx = r + lane;
+        w_src = 0;
+        w_dst = 0;
+        w_n = 0;
+        if (idx < a.nreq) {
+            if (FIXED) {
+                uint64_t s = 0;
+                int code = dev_locate(a.var, a.starts[idx], a.count, &s);
+                w_src = code ? 0 : s; // invalid request: keep its slot in the packed layout, copy nothing
+                w_dst = idx * nb;
+                w_n = nb;
+            } else {
+                w_src = a.req_src[idx];
+                w_dst = a.req_dst[idx];
+                w_n = a.req_dst[idx + 1] - w_dst;
+            }
+        }
+    }
+
+    // largest r in [0, nreq) with req_dst[r] <= pos, 32-ary search across the lanes
+    __device__ __forceinline__ int64_t locate_var(const GatherArgs &a, int64_t pos, int lane) {
+        int64_t lo = 0, hi = a.nreq;
+        while (hi - lo > 1) {
+            int64_t step = (hi - lo + 31) / 32;
+            int64_t idx = lo + (int64_t)(lane + 1) * step;
+            bool le = (idx < hi) && (a.req_dst[idx] <= pos);
+            int k = __popc(__ballot_sync(0xffffffffu, le));
+            lo = lo + (int64_t)k * step;
+            hi = min(hi, lo + step);
+        }
+        return lo;
+    }
+
+    __device__ __forceinline__ bool next(const GatherArgs &a, int lane, Chunk &c) {
+        while (true) {
+            if (seg_pos >= seg_end) {
+                unsigned int seg = 0;
+                if (lane == 0) seg = atomicAdd(&a.counters[0], 1u);
+                seg = __shfl_sync(0xffffffffu, seg, 0);
+                if ((int64_t)seg >= nseg) return false;
+                seg_pos = (int64_t)seg * seg_bytes;
+                seg_end = min(T, seg_pos + seg_bytes);
+                r = FIXED ? seg_pos / nb : locate_var(a, seg_pos, lane);
+            }
+            if (r >= a.nreq) { // defensive: cannot happen while seg_pos < T
+                seg_pos = seg_end;
+                continue;
+            }
+            if (r < win_base || r >= win_base + 32) load_window(a, lane);
+            int wl = (int)(r - win_base);
+            uint64_t src = __shfl_sync(0xffffffffu, w_src, wl);
+            int64_t d0 = __shfl_sync(0xffffffffu, w_dst, wl);
+            int64_t n = __shfl_sync(0xffffffffu, w_n, wl);
+            int64_t req_end = d0 + n;
+            if (req_end <= seg_pos) {
+                r++;
+                continue;
+            }
+            int64_t stop = min(req_end, seg_end);
+            int64_t len = min((int64_t)CH, stop - seg_pos);
+            c.src = src ? src + (uint64_t)(seg_pos - d0) : 0;
+            c.dpos = seg_pos;
+            c.n = (uint32_t)len;
+            seg_pos += len;
+            if (seg_pos >= req_end) r++;
+            if (src == 0) continue; // rejected request (FIXED): leave its slot untouched
+            return true;
+        }
+    }
+};
+
+#define DDS_FUNNEL4(W0, W1, W2, W3, W4)              \
+    out.x = __funnelshift_r(W0, W1, bs8);            \
+    out.y = __funnelshift_r(W1, W2, bs8);            \
+    out.z = __funnelshift_r(W2, W3, bs8);            \
+    out.w = __funnelshift_r(W3, W4, bs8);
+
+// Drain one staged chunk: payload byte k lives at shared address sb + a + k and goes to d[k].
+template <int CH>
+__device__ __forceinline__ void drain_chunk(uint32_t sb, uint32_t a, char *d, uint32_t n, int lane) {
+    uint32_t head = (16u - (uint32_t)((uint64_t)d & 15u)) & 15u;
+    if (head > n) head = n;
+    uint32_t nv = (n - head) >> 4;
+    uint32_t tail = n - head - (nv << 4);
+    uint32_t s = a + head; // shared offset of the first body byte, 0..30
+    uint32_t sh = s & 15u;
+    if (nv) {
+        if (sh == 0) {
+            // source and destination share the 16-byte phase: one bulk store moves the whole body
+            if (lane == 0) {
+                fence_proxy_async();
+                tma_store_1d(d + head, sb + s, nv << 4);
+            }
+        } else {
+            // re-phase through registers: two aligned 128-bit shared loads -> funnel shift -> aligned 128-bit store
+            const uint32_t q16 = s & ~15u;
+            const uint32_t ws = sh >> 2;
+            const uint32_t bs8 = (sh & 3u) * 8u;
+            char *dv = d + head;
+#pragma unroll 4
+            for (uint32_t j = (uint32_t)lane; j < nv; j += 32) {
+                uint4 lo = lds128(sb + q16 + (j << 4));
+                uint4 hi = lds128(sb + q16 + (j << 4) + 16);
+                uint4 out;
+                switch (ws) {
+                case 0: DDS_FUNNEL4(lo.x, lo.y, lo.z, lo.w, hi.x) break;
+                case 1: DDS_FUNNEL4(lo.y, lo.z, lo.w, hi.x, hi.y) break;
+                case 2: DDS_FUNNEL4(lo.z, lo.w, hi.x, hi.y, hi.z) break;
+                default: DDS_FUNNEL4(lo.w, hi.x, hi.y, hi.z, hi.w) break;
+                }
+                stg128(dv + ((size_t)j << 4), out);
+            }
+        }
+    }
+    if ((uint32_t)lane < head) d[lane] = (char)lds8(sb + a + (uint32_t)lane);
+    if ((uint32_t)lane < tail) {
+        uint32_t k = head + (nv << 4) + (uint32_t)lane;
+        d[k] = (char)lds8(sb + a + k);
+    }
+}
+
+template <bool FIXED, int NW, int S, int CH>
+__global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_constant__ GatherArgs a) {
+    constexpr int STAGE = CH + 32; // room for the aligned superset of a misaligned CH-byte range
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[NW][S];
+    __shared__ __align__(16) struct StageDesc {
+        int64_t dpos;
+        uint32_t n, a;
+    } desc[NW][S];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * NW + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * NW;
+
+    // ---- total bytes, segment geometry -------------------------------------------------------
+    ChunkWalker<FIXED, CH> w;
+    w.nb = FIXED ? a.count * a.var.row_bytes : 0;
+    w.T = FIXED ? w.nb * a.nreq : a.req_dst[a.nreq];
+    bool over = w.T > a.dst_cap;
+    {
+        int64_t target = w.T / (nwarps * 8);
+        target = max((int64_t)CH, min(target, (int64_t)1 << 20));
+        if (FIXED && w.nb > 0 && w.nb <= target)
+            w.seg_bytes = (target / w.nb) * w.nb; // whole requests per segment
+        else
+            w.seg_bytes = (target / CH) * CH;
+        w.nseg = w.T > 0 ? (w.T + w.seg_bytes - 1) / w.seg_bytes : 0;
+    }
+    if (over) {
+        if (gwarp == 0 && lane == 0) report(a.status, a.nreq, DDSK_CODE_CAPACITY);
+        w.nseg = 0;
+    }
+
+    // ---- FIXED: validation pass (the reference's two checks, for EVERY request, even zero-byte ones)
+    if (FIXED) {
+        for (int64_t i = gwarp * 32 + lane; i < a.nreq; i += nwarps * 32) {
+            uint64_t s;
+            int code = dev_locate(a.var, a.starts[i], a.count, &s);
+            if (code) report(a.status, i, code);
+            if (a.offsets_out) a.offsets_out[i] = i * w.nb;
+        }
+        if (a.offsets_out && gwarp == 0 && lane == 0) a.offsets_out[a.nreq] = w.T;
+    }
+
+    // ---- per-warp pipeline -------------------------------------------------------------------
+    const uint32_t ring = smem_u32(smem_dyn) + (uint32_t)warp * (uint32_t)(S * STAGE);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[warp][s]), 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    uint32_t issued = 0, consumed = 0;
+    bool more = w.nseg > 0;
+    while (true) {
+        // issue up to S-1 chunks ahead
+        while (more && issued - consumed < (uint32_t)(S - 1)) {
+            Chunk c;
+            if (!w.next(a, lane, c)) {
+                more = false;
+                break;
+            }
+            const uint32_t st = issued % S;
+            if (lane == 0) {
+                // the stage's previous tenant was drained >= 2 consumes ago; its bulk store (if any) is
+                // at most the second most recent group of this thread
+                bulk_wait_read<1>();
+                const uint32_t al = (uint32_t)(c.src & 15u);
+                const uint32_t sz = (al + c.n + 15u) & ~15u;
+                desc[warp][st].dpos = c.dpos;
+                desc[warp][st].n = c.n;
+                desc[warp][st].a = al;
+                const uint32_t bar = smem_u32(&full_bar[warp][st]);
+                mbar_expect_tx(bar, sz);
+                tma_load_1d(ring + st * STAGE, (const void *)(c.src - al), sz, bar);
+            }
+            issued++;
+        }
+        if (consumed == issued) break;
+        // drain the oldest chunk
+        const uint32_t st = consumed % S;
+        const uint32_t parity = (consumed / S) & 1u;
+        const uint32_t bar = smem_u32(&full_bar[warp][st]);
+        if (!mbar_try_wait(bar, parity)) {
+            const uint64_t t0 = globaltimer_ns();
+            while (!mbar_try_wait(bar, parity)) {
+                if (globaltimer_ns() - t0 > 4000000000ull) { // 4 s: a lost TMA completion must not hang the box
+                    report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+        const int64_t dpos = desc[warp][st].dpos;
+        const uint32_t n = desc[warp][st].n;
+        const uint32_t al = desc[warp][st].a;
+        drain_chunk<CH>(ring + st * STAGE, al, a.dst + dpos, n, lane);
+        if (lane == 0) bulk_commit(); // one (possibly empty) group per drained chunk
+        __syncwarp();                 // all lanes are done reading the stage before it is refilled
+        consumed++;
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+
+    // ---- self-resetting ticket counters ------------------------------------------------------
+    if (lane == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(&a.counters[1], 1u);
+        if (done == (unsigned int)(nwarps - 1)) {
+            a.counters[0] = 0;
+            a.counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan kernels (variable counts): lookup + checks + exclusive scan of request bytes
+// ------------------------------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 256;
+constexpr int PLAN_ITEMS = 4;
+constexpr int PLAN_TILE = PLAN_THREADS * PLAN_ITEMS;
+
+__device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int64_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
+    __shared__ int64_t warp_tot[PLAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int64_t base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_THREADS / 32; k++) {
+        int64_t t = warp_tot[k];
+        if (k < wid) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+// pass 1: per request source address + byte size (size parked in req_dst), per tile byte sum
+__global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __grid_constant__ ddsk_var_t var,
+                                                                       const int64_t *__restrict__ starts,
+                                                                       const int64_t *__restrict__ counts, int64_t nreq,
+                                                                       uint64_t *__restrict__ req_src,
+                                                                       int64_t *__restrict__ req_dst,
+                                                                       int64_t *__restrict__ tile_sums,
+                                                                       unsigned long long *status) {
+    const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_ITEMS; k++) {
+        int64_t i = base + (int64_t)k * PLAN_THREADS + threadIdx.x;
+        if (i < nreq) {
+            uint64_t s = 0;
+            int64_t c = counts[i];
+            int code = dev_locate(var, starts[i], c, &s);
+            int64_t nbytes = 0;
+            if (code) {
+                report(status, i, code);
+                s = 0;
+            } else {
+                nbytes = c * var.row_bytes;
+            }
+            req_src[i] = s;
+            req_dst[i] = nbytes;
+            mine += nbytes;
+        }
+    }
+    int64_t tot;
+    block_excl_scan(mine, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// pass 2: exclusive scan. Each CTA sums the tiles before it, then scans its own tile in place.
+__global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nreq, int64_t *__restrict__ req_dst,
+                                                                     const int64_t *__restrict__ tile_sums,
+                                                                     int64_t *__restrict__ offsets_out) {
+    int64_t part = 0;
+    for (int64_t t = threadIdx.x; t < (int64_t)blockIdx.x; t += PLAN_THREADS) part += tile_sums[t];
+    int64_t tile_base;
+    block_excl_scan(part, &tile_base);
+    // layout inside a tile is striped (item k of thread t = k*THREADS + t): scan stripe by stripe
+    const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
+    int64_t running = tile_base;
+#pragma unroll
+    for (int k = 0; k < PLAN_ITEMS; k++) {
+        int64_t i = base + (int64_t)k * PLAN_THREADS + threadIdx.x;
+        int64_t v = i < nreq ? req_dst[i] : 0;
+        int64_t tot;
+        int64_t ex = block_excl_scan(v, &tot);
+        if (i < nreq) {
+            req_dst[i] = running + ex;
+            if (offsets_out) offsets_out[i] = running + ex;
+        }
+        running += tot;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        req_dst[nreq] = running;
+        if (offsets_out) offsets_out[nreq] = running;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic payload generator (bench / test helper)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <typename T>
+__global__ void dds_synth_kernel(T *__restrict__ base, uint64_t first_elem, uint64_t nelem, uint64_t seed) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nelem; i += (uint64_t)gridDim.x * blockDim.x)
+        base[i] = (T)splitmix64(seed ^ (first_elem + i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch geometry
+// ------------------------------------------------------------------------------------------------
+struct Geometry {
+    int nw, stages, ch;
+};
+constexpr Geometry kGeoms[] = {{8, 4, 4096}, {8, 6, 4096}, {16, 3, 4096}, {4, 4, 8192}, {12, 4, 4096}, {4, 6, 4096}};
+
+int g_geom = -1;
+int g_sms = 0;
+int g_ctas_per_sm = 1;
+
+int pick_geometry() {
+    if (g_geom >= 0) return 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    int g = 0;
+    if (const char *e = getenv("DDS_GATHER_GEOM")) g = atoi(e); // tuning knob (kernel variants, not backends)
+    if (g < 0 || g >= (int)(sizeof(kGeoms) / sizeof(kGeoms[0]))) g = 0;
+    if (const char *e = getenv("DDS_GATHER_CTAS_PER_SM")) g_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
+    g_geom = g;
+    return 0;
+}
+
+template <bool FIXED, int NW, int S, int CH>
+int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
+    constexpr int smem = NW * S * (CH + 32);
+    static bool configured = false;
+    auto kern = dds_gather_kernel<FIXED, NW, S, CH>;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int per_sm = g_ctas_per_sm;
+    while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;
+    kern<<<g_sms * per_sm, NW * 32, smem, stream>>>(args);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <bool FIXED>
+int launch_gather(const GatherArgs &args, cudaStream_t stream) {
+    if (int rc = pick_geometry()) return rc;
+    switch (g_geom) {
+    case 1: return launch_gather_t<FIXED, 8, 6, 4096>(args, stream);
+    case 2: return launch_gather_t<FIXED, 16, 3, 4096>(args, stream);
+    case 3: return launch_gather_t<FIXED, 4, 4, 8192>(args, stream);
+    case 4: return launch_gather_t<FIXED, 12, 4, 4096>(args, stream);
+    case 5: return launch_gather_t<FIXED, 4, 6, 4096>(args, stream);
+    default: return launch_gather_t<FIXED, 8, 4, 4096>(args, stream);
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the thin C-ABI the host C++ calls
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *ddsk_last_cuda_error(void) { return g_cuda_err; }
+unsigned long long ddsk_launch_count(void) { return g_launches.load(); }
+
+void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes) {
+    if (pick_geometry()) {
+        *ctas = *warps_per_cta = *stages = *chunk_bytes = *smem_bytes = 0;
+        return;
+    }
+    const Geometry &g = kGeoms[g_geom];
+    int smem = g.nw * g.stages * (g.ch + 32);
+    int per_sm = g_ctas_per_sm;
+    while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;
+    *ctas = g_sms * per_sm;
+    *warps_per_cta = g.nw;
+    *stages = g.stages;
+    *chunk_bytes = g.ch;
+    *smem_bytes = smem;
+}
+
+int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,
+                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                      void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (nreq <= 0) return 0;
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.var = *var;
+    a.starts = starts_dev;
+    a.count = count;
+    a.nreq = nreq;
+    a.dst = (char *)dst_dev;
+    a.dst_cap = dst_capacity;
+    a.offsets_out = offsets_dev_or_null;
+    a.status = scr->status;
+    a.counters = scr->counters;
+    return launch_gather<true>(a, st);
+}
+
+int ddsk_gather_var(const ddsk_var_t *var, const int64_t *starts_dev, const int64_t *counts_dev, int64_t nreq,
+                    void *dst_dev, int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr,
+                    int reset_status, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (nreq <= 0) return 0;
+    if (nreq > scr->cap_req) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_var: scratch too small (%lld > %lld)", (long long)nreq,
+                 (long long)scr->cap_req);
+        return -2;
+    }
+    const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
+    dds_plan_lookup_kernel<<<tiles, PLAN_THREADS, 0, st>>>(*var, starts_dev, counts_dev, nreq, scr->req_src, scr->req_dst,
+                                                           scr->tile_sums, scr->status);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    dds_plan_scan_kernel<<<tiles, PLAN_THREADS, 0, st>>>(nreq, scr->req_dst, scr->tile_sums, offsets_dev_or_null);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.var = *var;
+    a.req_src = scr->req_src;
+    a.req_dst = scr->req_dst;
+    a.nreq = nreq;
+    a.dst = (char *)dst_dev;
+    a.dst_cap = dst_capacity;
+    a.status = scr->status;
+    a.counters = scr->counters;
+    return launch_gather<false>(a, st);
+}
+
+int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int64_t disp, int itemsize, uint64_t seed,
+                    void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t nelem = (uint64_t)nrows * (uint64_t)disp;
+    uint64_t first = (uint64_t)first_global_row * (uint64_t)disp;
+    if (nelem == 0) return 0;
+    int blocks = (int)((nelem + 255) / 256 < 148 * 16 ? (nelem + 255) / 256 : 148 * 16);
+    switch (itemsize) {
+    case 1: dds_synth_kernel<uint8_t><<<blocks, 256, 0, st>>>((uint8_t *)base_dev, first, nelem, seed); break;
+    case 2: dds_synth_kernel<uint16_t><<<blocks, 256, 0, st>>>((uint16_t *)base_dev, first, nelem, seed); break;
+    case 4: dds_synth_kernel<uint32_t><<<blocks, 256, 0, st>>>((uint32_t *)base_dev, first, nelem, seed); break;
+    case 8: dds_synth_kernel<uint64_t><<<blocks, 256, 0, st>>>((uint64_t *)base_dev, first, nelem, seed); break;
+    default:
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_synth_fill: unsupported itemsize %d", itemsize);
+        return -2;
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

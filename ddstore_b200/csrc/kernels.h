@@ -1,0 +1,70 @@
+/* ddstore_b200/csrc/kernels.h -- the thin C-ABI between the host C++ store (store.cpp) and the
+ * CUDA side (kernels.cu). Plain pointers, sizes and a cudaStream_t passed as void*. Nothing here
+ * is public; the public boundary is include/ddstore_b200.h. */
+#ifndef DDSK_KERNELS_H
+#define DDSK_KERNELS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDSK_MAX_RANKS 64
+
+/* Device-visible description of one variable: what the reference keeps in VarInfo
+ * (/root/reference/include/ddstore.hpp:10-22) minus the MPI window, plus the peer-mapped shard base
+ * of every owner (the "window"). Passed BY VALUE as a kernel parameter (constant bank). */
+typedef struct ddsk_var {
+    const void *bases[DDSK_MAX_RANKS]; /* shard base of rank r as mapped into THIS process (IPC / peer) */
+    int64_t lenlist[DDSK_MAX_RANKS];   /* inclusive cumulative row counts, ddstore.hpp:84-89 */
+    int64_t row_bytes;                 /* disp * itemsize, the window's disp_unit, ddstore.hpp:58 */
+    int32_t nranks;
+    int32_t pad_;
+} ddsk_var_t;
+
+/* status word written by the kernels: 0xFFFF... = ok, else (first_bad_request << 8) | code */
+#define DDSK_STATUS_OK 0xFFFFFFFFFFFFFFFFull
+#define DDSK_CODE_START 2
+#define DDSK_CODE_COUNT 3
+#define DDSK_CODE_CAPACITY 12
+#define DDSK_CODE_WATCHDOG 14
+
+/* scratch a store owns for the batched path (all device memory) */
+typedef struct ddsk_scratch {
+    unsigned long long *status; /* 1 word */
+    unsigned int *counters;     /* 4 words: [0] segment ticket, [1] finished warps (self-resetting) */
+    uint64_t *req_src;          /* [cap_req]   planned source address per request (0 = skip) */
+    int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
+    int64_t *tile_sums;         /* [cap_req/PLAN_TILE + 1] */
+    int64_t cap_req;
+} ddsk_scratch_t;
+
+/* Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
+ * One launch: validate + owner lookup + gather + pack. */
+int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,
+                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                      void *stream);
+
+/* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. */
+int ddsk_gather_var(const ddsk_var_t *var, const int64_t *starts_dev, const int64_t *counts_dev, int64_t nreq,
+                    void *dst_dev, int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr,
+                    int reset_status, void *stream);
+
+/* Synthetic payload: element (global_row g, col c) = low itemsize bytes of
+ * splitmix64(seed ^ (g*disp + c)). Bench / test helper, fills a local shard in place. */
+int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int64_t disp, int itemsize, uint64_t seed,
+                    void *stream);
+
+/* launch geometry actually used (for bench reporting / DESIGN.md) */
+void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long ddsk_launch_count(void);
+
+const char *ddsk_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,695 @@
+// ddstore_b200/csrc/store.cpp -- host side of the store: the reference's `class DDStore`
+// (/root/reference/include/ddstore.hpp:26-258, src/ddstore.cxx:19-96) re-built for B200:
+//   * a variable's shard is a cudaMalloc'd block of this rank's HBM (reference: MPI_Alloc_mem + memcpy,
+//     ddstore.hpp:44-49);
+//   * the "window" is the table of every rank's shard base mapped into this process through CUDA IPC
+//     (reference: MPI_Win_create, ddstore.hpp:56-61) -- NVSwitch makes every peer equally near;
+//   * lenlist / disp bookkeeping is the reference's (ddstore.hpp:75-89);
+//   * get() is a launch of the batched-gather kernel in kernels.cu (reference: MPI_Win_lock / MPI_Get /
+//     MPI_Win_unlock per sample, ddstore.hpp:222-237);
+//   * epoch_begin/epoch_end are stream-sync + barrier with the reference's state machine
+//     (MPI_Win_fence, ddstore.cxx:51-77).
+// All CUDA work goes through the CUDA runtime C API and the ddsk_* launchers (kernels.h).
+// There is no CPU data path: if no device is usable, dds_create fails with DDS_ERR_NO_DEVICE.
+#include <cuda_runtime_api.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ddstore_b200.h"
+#include "internal.h"
+#include "kernels.h"
+
+
+namespace {
+
+thread_local std::string g_err;
+
+const char *code_text(int code) {
+    switch (code) {
+    case DDS_OK: return "";
+    case DDS_ERR_DTYPE: return "Invalid data type";
+    case DDS_ERR_START: return "Invalid start on target";
+    case DDS_ERR_COUNT: return "Invalid count on target";
+    case DDS_ERR_DISP: return "Invalid disp";
+    case DDS_ERR_FENCE_ACTIVE: return "Fence already activated";
+    case DDS_ERR_FENCE_INACTIVE: return "Fence is not activated";
+    case DDS_ERR_UNKNOWN_VAR: return "Unknown variable";
+    case DDS_ERR_EXISTS: return "Variable already exists";
+    case DDS_ERR_CUDA: return "CUDA error";
+    case DDS_ERR_COMM: return "Communicator error";
+    case DDS_ERR_ARG: return "Invalid argument";
+    case DDS_ERR_CAPACITY: return "Destination buffer too small for the packed batch";
+    case DDS_ERR_NO_DEVICE: return "No usable CUDA device (ddstore_b200 has no CPU fallback)";
+    case DDS_ERR_WATCHDOG: return "Gather kernel watchdog fired";
+    default: return "Unknown error";
+    }
+}
+
+} // namespace
+
+namespace dds_internal {
+int fail(int code, const std::string &detail) {
+    // codes 1-6 keep the reference's exception text EXACTLY; the others append detail
+    g_err = code_text(code);
+    if (code > DDS_ERR_FENCE_INACTIVE && !detail.empty()) g_err += ": " + detail;
+    return code;
+}
+void clear_error() { g_err.clear(); }
+} // namespace dds_internal
+
+using dds_internal::clear_error;
+using dds_internal::fail;
+
+namespace {
+
+int cuda_fail(cudaError_t e, const char *what) {
+    char buf[384];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+        return fail(DDS_ERR_NO_DEVICE, buf);
+    return fail(DDS_ERR_CUDA, buf);
+}
+#define CU(expr)                                     \
+    do {                                             \
+        cudaError_t e__ = (expr);                    \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+struct PeerRec { // what every rank publishes in add()/init(): the reference's Allgather(nrows) + Allreduce(disp)
+                 // + Win_create rolled into one exchange
+    int64_t nrows;
+    int32_t disp;
+    int32_t itemsize;
+    int32_t pid;
+    int32_t device;
+    uint64_t raw_ptr;
+    uint64_t host_tag;
+    cudaIpcMemHandle_t handle;
+};
+
+struct Var {
+    std::string name;
+    int itemsize = 0;
+    int disp = 0;
+    int64_t nrows = 0; // local
+    std::vector<int64_t> lenlist;
+    void *base = nullptr; // local shard (device)
+    size_t bytes = 0;
+    std::vector<void *> peer_base;  // as mapped here
+    std::vector<char> peer_opened;  // 1 = cudaIpcOpenMemHandle'd (must be closed)
+    bool fence_active = false;
+    ddsk_var_t kv;
+};
+
+} // namespace
+
+struct dds_store {
+    dds_comm_t *comm = nullptr;
+    int rank = 0, size = 1, device = 0, method = 0;
+    cudaStream_t stream = nullptr;
+    std::map<std::string, Var> vars;
+    std::vector<void *> zombies; // shards of failed add()s, kept until free so no peer mapping dangles
+    // scratch for the batched path
+    ddsk_scratch_t scr;
+    int64_t *d_starts = nullptr, *d_counts = nullptr;
+    int64_t idx_cap = 0;
+    void *d_out = nullptr;
+    int64_t out_cap = 0;
+    unsigned long long *h_status = nullptr; // pinned: [0] status, [1] total bytes
+    // pending async batch
+    bool pending = false;
+    cudaStream_t pending_stream = nullptr;
+    int64_t pending_fixed_total = -1;
+};
+
+namespace {
+
+uint64_t host_tag() {
+    char buf[256] = {0};
+    gethostname(buf, sizeof(buf) - 1);
+    uint64_t h = 1469598103934665603ull;
+    for (char *p = buf; *p; p++) h = (h ^ (unsigned char)*p) * 1099511628211ull;
+    return h;
+}
+
+int ensure_scratch(dds_store *s, int64_t nreq) {
+    if (nreq <= s->scr.cap_req) return DDS_OK;
+    int64_t cap = std::max<int64_t>(4096, s->scr.cap_req);
+    while (cap < nreq) cap *= 2;
+    if (s->scr.req_src) cudaFree(s->scr.req_src);
+    if (s->scr.req_dst) cudaFree(s->scr.req_dst);
+    if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
+    s->scr.req_src = nullptr;
+    s->scr.req_dst = nullptr;
+    s->scr.tile_sums = nullptr;
+    s->scr.cap_req = 0;
+    CU(cudaMalloc((void **)&s->scr.req_src, (size_t)cap * 8));
+    CU(cudaMalloc((void **)&s->scr.req_dst, (size_t)(cap + 1) * 8));
+    CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+    s->scr.cap_req = cap;
+    return DDS_OK;
+}
+
+int ensure_idx(dds_store *s, int64_t nreq) {
+    if (nreq <= s->idx_cap) return DDS_OK;
+    int64_t cap = std::max<int64_t>(4096, s->idx_cap);
+    while (cap < nreq) cap *= 2;
+    if (s->d_starts) cudaFree(s->d_starts);
+    if (s->d_counts) cudaFree(s->d_counts);
+    s->d_starts = s->d_counts = nullptr;
+    s->idx_cap = 0;
+    CU(cudaMalloc((void **)&s->d_starts, (size_t)cap * 8));
+    CU(cudaMalloc((void **)&s->d_counts, (size_t)cap * 8));
+    s->idx_cap = cap;
+    return DDS_OK;
+}
+
+int ensure_out(dds_store *s, int64_t bytes) {
+    if (bytes <= s->out_cap) return DDS_OK;
+    int64_t cap = std::max<int64_t>(1 << 20, s->out_cap);
+    while (cap < bytes) cap *= 2;
+    if (s->d_out) cudaFree(s->d_out);
+    s->d_out = nullptr;
+    s->out_cap = 0;
+    CU(cudaMalloc(&s->d_out, (size_t)cap));
+    s->out_cap = cap;
+    return DDS_OK;
+}
+
+Var *find_var(dds_store *s, const char *name) {
+    if (!name) return nullptr;
+    auto it = s->vars.find(name);
+    return it == s->vars.end() ? nullptr : &it->second;
+}
+
+void release_var(Var &v, int rank) {
+    for (size_t r = 0; r < v.peer_base.size(); r++)
+        if ((int)r != rank && v.peer_opened[r] && v.peer_base[r]) cudaIpcCloseMemHandle(v.peer_base[r]);
+    v.peer_base.clear();
+    v.peer_opened.clear();
+}
+
+// add() and init() share everything but the fill (ddstore.hpp:39-108 vs :110-179)
+int register_var(dds_store *s, const char *name, const void *buffer, int64_t nrows, int disp, int itemsize,
+                 int buffer_on_device, bool zero_fill) {
+    if (!s || !name) return fail(DDS_ERR_ARG, "null store or name");
+    if (nrows < 0 || disp < 0 || itemsize <= 0) return fail(DDS_ERR_ARG, "negative nrows/disp or itemsize <= 0");
+    if (s->size > DDSK_MAX_RANKS) return fail(DDS_ERR_ARG, "communicator larger than DDSK_MAX_RANKS");
+    if (!zero_fill && !buffer && nrows * (int64_t)disp > 0) return fail(DDS_ERR_ARG, "null buffer");
+    CU(cudaSetDevice(s->device));
+    const bool exists = s->vars.count(name) != 0;
+
+    // shard: payload + 16 bytes of slack so the kernel's 16-byte-aligned superset loads never leave it
+    const size_t payload = (size_t)nrows * (size_t)disp * (size_t)itemsize;
+    const size_t alloc = ((payload + 16 + 255) / 256) * 256;
+    void *base = nullptr;
+    CU(cudaMalloc(&base, alloc));
+    if (zero_fill || payload == 0) {
+        CU(cudaMemsetAsync(base, 0, alloc, s->stream));
+    } else {
+        CU(cudaMemsetAsync((char *)base + payload, 0, alloc - payload, s->stream));
+        CU(cudaMemcpyAsync(base, buffer, payload, buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+
+    PeerRec mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.nrows = nrows;
+    mine.disp = disp;
+    mine.itemsize = itemsize;
+    mine.pid = (int32_t)getpid();
+    mine.device = s->device;
+    mine.raw_ptr = (uint64_t)base;
+    mine.host_tag = host_tag();
+    if (s->size > 1) CU(cudaIpcGetMemHandle(&mine.handle, base));
+    std::vector<PeerRec> all((size_t)s->size);
+    if (int rc = dds_comm_allgather(s->comm, &mine, all.data(), sizeof(PeerRec))) {
+        cudaFree(base);
+        return rc;
+    }
+
+    // ddstore.hpp:78-82: every rank must pass the same disp; the ranks that differ from the max throw
+    int max_disp = 0;
+    for (auto &p : all) max_disp = std::max(max_disp, (int)p.disp);
+    bool bad_disp = max_disp != disp;
+    bool bad_item = false;
+    for (auto &p : all) bad_item |= p.itemsize != itemsize;
+    if (bad_disp || bad_item || exists) {
+        s->zombies.push_back(base); // peers may have mapped it already; released in dds_free
+        (void)dds_comm_barrier(s->comm); // stay in step with the ranks that succeed
+        if (bad_disp) return fail(DDS_ERR_DISP);
+        if (bad_item) return fail(DDS_ERR_DTYPE);
+        return fail(DDS_ERR_EXISTS, name);
+    }
+
+    Var v;
+    v.name = name;
+    v.itemsize = itemsize;
+    v.disp = disp;
+    v.nrows = nrows;
+    v.base = base;
+    v.bytes = alloc;
+    v.lenlist.resize((size_t)s->size);
+    int64_t sum = 0; // ddstore.hpp:84-89 inclusive running sum
+    for (int r = 0; r < s->size; r++) {
+        sum += all[(size_t)r].nrows;
+        v.lenlist[(size_t)r] = sum;
+    }
+    v.peer_base.assign((size_t)s->size, nullptr);
+    v.peer_opened.assign((size_t)s->size, 0);
+    for (int r = 0; r < s->size; r++) {
+        const PeerRec &p = all[(size_t)r];
+        if (r == s->rank) {
+            v.peer_base[(size_t)r] = base;
+        } else if (p.host_tag == mine.host_tag && p.pid == mine.pid) {
+            // thread-ranks of one process: the raw pointer is already valid here
+            if (p.device != s->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, s->device, p.device));
+                if (!can) return fail(DDS_ERR_CUDA, "peer GPUs of one process cannot access each other");
+                cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                (void)cudaGetLastError();
+            }
+            v.peer_base[(size_t)r] = (void *)p.raw_ptr;
+        } else {
+            if (p.host_tag != mine.host_tag)
+                return fail(DDS_ERR_COMM, "ranks on different hosts: the store spans one NVSwitch box (use one store per box)");
+            void *mapped = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&mapped, p.handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+            v.peer_base[(size_t)r] = mapped;
+            v.peer_opened[(size_t)r] = 1;
+        }
+    }
+    memset(&v.kv, 0, sizeof(v.kv));
+    for (int r = 0; r < s->size; r++) {
+        v.kv.bases[r] = v.peer_base[(size_t)r];
+        v.kv.lenlist[r] = v.lenlist[(size_t)r];
+    }
+    v.kv.row_bytes = (int64_t)disp * (int64_t)itemsize;
+    v.kv.nranks = s->size;
+    s->vars.emplace(v.name, std::move(v));
+    // every shard is filled and mapped before anyone may read it
+    return dds_comm_barrier(s->comm);
+}
+
+int decode_status(unsigned long long st, int64_t *bad_index) {
+    if (st == DDSK_STATUS_OK) {
+        if (bad_index) *bad_index = -1;
+        return DDS_OK;
+    }
+    int code = (int)(st & 0xFFull);
+    if (bad_index) *bad_index = (int64_t)(st >> 8);
+    switch (code) {
+    case DDSK_CODE_START: return fail(DDS_ERR_START);
+    case DDSK_CODE_COUNT: return fail(DDS_ERR_COUNT);
+    case DDSK_CODE_CAPACITY:
+        if (bad_index) *bad_index = -1;
+        return fail(DDS_ERR_CAPACITY);
+    default: return fail(DDS_ERR_WATCHDOG);
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char *dds_last_error(void) { return g_err.c_str(); }
+const char *dds_strerror(int code) { return code_text(code); }
+
+// ---------------------------------------------------------------- host-side index math
+int dds_sortedsearch(const int64_t *lenlist, int nranks, int64_t num) {
+    // src/ddstore.cxx:5-17
+    int rtn = 0;
+    for (int i = 1; i < nranks; i++)
+        if (lenlist[i - 1] <= num && num < lenlist[i]) {
+            rtn = i;
+            break;
+        }
+    return rtn;
+}
+
+int dds_locate(const int64_t *lenlist, int nranks, int64_t start, int64_t count, int *owner, int64_t *offset) {
+    // include/ddstore.hpp:205-214
+    int t = dds_sortedsearch(lenlist, nranks, start);
+    int64_t off = t > 0 ? lenlist[t - 1] : 0;
+    if (owner) *owner = t;
+    if (offset) *offset = off;
+    if (start < off) return fail(DDS_ERR_START);
+    if (count < 0 || start + count > lenlist[t]) return fail(DDS_ERR_COUNT);
+    return DDS_OK;
+}
+
+int dds_exchange_lenlist(dds_comm_t *c, int64_t nrows, int disp, int64_t *lenlist) {
+    // include/ddstore.hpp:75-89
+    if (!c || !lenlist) return fail(DDS_ERR_ARG, "null communicator or lenlist");
+    const int n = dds_comm_size(c);
+    int64_t mine[2] = {nrows, (int64_t)disp};
+    std::vector<int64_t> all((size_t)n * 2);
+    if (int rc = dds_comm_allgather(c, mine, all.data(), sizeof(mine))) return rc;
+    int64_t max_disp = 0, sum = 0;
+    for (int r = 0; r < n; r++) max_disp = std::max(max_disp, all[(size_t)r * 2 + 1]);
+    for (int r = 0; r < n; r++) {
+        sum += all[(size_t)r * 2];
+        lenlist[r] = sum;
+    }
+    if (max_disp != disp) return fail(DDS_ERR_DISP);
+    return DDS_OK;
+}
+
+// ---------------------------------------------------------------- lifecycle
+dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
+    clear_error();
+    if (!comm) {
+        fail(DDS_ERR_ARG, "null communicator");
+        return nullptr;
+    }
+    if (method != 0 && method != 1) {
+        fail(DDS_ERR_ARG, "method must be 0 or 1 (both select the NVLink transport)");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        fail(DDS_ERR_NO_DEVICE, e != cudaSuccess ? cudaGetErrorString(e) : "cudaGetDeviceCount returned 0");
+        return nullptr;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) {
+        fail(DDS_ERR_ARG, "device ordinal out of range");
+        return nullptr;
+    }
+    dds_store *s = new dds_store;
+    memset(&s->scr, 0, sizeof(s->scr));
+    s->comm = comm;
+    s->rank = dds_comm_rank(comm);
+    s->size = dds_comm_size(comm);
+    s->device = device;
+    s->method = method;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc((void **)&s->scr.status, 8) == cudaSuccess &&
+              cudaMalloc((void **)&s->scr.counters, 16) == cudaSuccess &&
+              cudaMemset(s->scr.counters, 0, 16) == cudaSuccess &&
+              cudaMallocHost((void **)&s->h_status, 16) == cudaSuccess;
+    if (!ok) {
+        cuda_fail(cudaGetLastError(), "dds_create: device setup");
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
+int dds_rank(const dds_store_t *s) { return s ? s->rank : -1; }
+int dds_size(const dds_store_t *s) { return s ? s->size : -1; }
+
+int dds_add(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int disp, int itemsize,
+            int buffer_on_device) {
+    clear_error();
+    return register_var(s, name, buffer, nrows, disp, itemsize, buffer_on_device, false);
+}
+
+int dds_init(dds_store_t *s, const char *name, int64_t nrows, int disp, int itemsize) {
+    clear_error();
+    return register_var(s, name, nullptr, nrows, disp, itemsize, 0, true);
+}
+
+int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
+               int buffer_on_device) {
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE); // ddstore.hpp:189-190
+    if (nrows < 0 || offset < 0 || offset + nrows > v->nrows)
+        return fail(DDS_ERR_ARG, "update outside the local shard (unchecked memcpy in the reference)");
+    CU(cudaSetDevice(s->device));
+    const size_t row = (size_t)v->disp * (size_t)v->itemsize;
+    if (nrows * (int64_t)row > 0) {
+        CU(cudaMemcpyAsync((char *)v->base + (size_t)offset * row, buffer, (size_t)nrows * row,
+                           buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return DDS_OK;
+}
+
+int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const int64_t *counts,
+                  int64_t fixed_count, int64_t nreq, int itemsize, void *dst, int64_t dst_capacity,
+                  int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
+                  int64_t *bad_index) {
+    clear_error();
+    if (bad_index) *bad_index = -1;
+    if (total_bytes) *total_bytes = 0;
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE); // ddstore.hpp:202-203
+    if (nreq < 0 || dst_capacity < 0) return fail(DDS_ERR_ARG, "negative nreq or capacity");
+    if (nreq > 0 && !starts) return fail(DDS_ERR_ARG, "null starts");
+    const bool idx_dev = flags & DDS_IDX_ON_DEVICE, dst_dev = flags & DDS_DST_ON_DEVICE;
+    const bool no_sync = flags & DDS_NO_SYNC;
+    if (no_sync && !(idx_dev && dst_dev)) return fail(DDS_ERR_ARG, "async batches need device indices and a device destination");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    // Async batches may queue up behind each other on ONE stream (the status word is then sticky: the first
+    // error of the whole queue is what dds_batch_wait reports). Anything else drains the queue first.
+    const bool chain = s->pending && no_sync && st == s->pending_stream;
+    if (s->pending && !chain) {
+        if (int rc = dds_batch_wait(s, nullptr, nullptr)) return rc;
+    }
+    const int64_t R = v->kv.row_bytes;
+    const bool fixed = counts == nullptr;
+
+    if (nreq == 0) {
+        if (dst_offsets) {
+            int64_t z = 0;
+            if (dst_dev) CU(cudaMemcpyAsync(dst_offsets, &z, 8, cudaMemcpyHostToDevice, st));
+            else dst_offsets[0] = 0;
+            if (dst_dev) CU(cudaStreamSynchronize(st));
+        }
+        return DDS_OK;
+    }
+
+    // ---- indices to the device (16 B per request)
+    const int64_t *d_starts = starts, *d_counts = counts;
+    if (!idx_dev) {
+        if (int rc = ensure_idx(s, nreq)) return rc;
+        CU(cudaMemcpyAsync(s->d_starts, starts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
+        d_starts = s->d_starts;
+        if (!fixed) {
+            CU(cudaMemcpyAsync(s->d_counts, counts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
+            d_counts = s->d_counts;
+        }
+    }
+    if (!fixed) {
+        if (int rc = ensure_scratch(s, nreq)) return rc;
+    }
+
+    // ---- packed size as far as the host can know it
+    int64_t upper = -1; // upper bound of the packed bytes (== total when every request is valid)
+    if (fixed)
+        upper = fixed_count > 0 ? nreq * fixed_count * R : 0;
+    else if (!idx_dev) {
+        upper = 0;
+        for (int64_t i = 0; i < nreq; i++) upper += counts[i] > 0 ? counts[i] * R : 0;
+    }
+
+    // ---- destination: the caller's device buffer, or the store's staging buffer for a host destination
+    void *d_dst = dst;
+    int64_t cap = dst_capacity;
+    if (!dst_dev) {
+        int64_t need = upper >= 0 ? std::min(upper, dst_capacity) : dst_capacity;
+        if (int rc = ensure_out(s, std::max<int64_t>(need, 16))) return rc;
+        d_dst = s->d_out;
+        cap = need;
+    }
+    if (!d_dst && cap > 0) return fail(DDS_ERR_ARG, "null destination");
+
+    // ---- launch
+    int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
+    int krc;
+    if (fixed)
+        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, !chain, st);
+    else
+        krc = ddsk_gather_var(&v->kv, d_starts, d_counts, nreq, d_dst, cap, d_offsets, &s->scr, !chain, st);
+    if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+
+    CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
+    if (!fixed) CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[nreq], 8, cudaMemcpyDeviceToHost, st));
+    s->pending_fixed_total = fixed ? upper : -1;
+
+    if (no_sync) {
+        s->pending = true;
+        s->pending_stream = st;
+        return DDS_OK;
+    }
+
+    // ---- results back to a host destination
+    if (!dst_dev) {
+        if (upper >= 0) {
+            if (cap > 0) CU(cudaMemcpyAsync(dst, d_dst, (size_t)cap, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaStreamSynchronize(st)); // device-resident counts: the size is only known on the device
+            int64_t tot = (int64_t)s->h_status[1];
+            if (s->h_status[0] == DDSK_STATUS_OK && tot > 0 && tot <= cap)
+                CU(cudaMemcpyAsync(dst, d_dst, (size_t)tot, cudaMemcpyDeviceToHost, st));
+        }
+        if (dst_offsets) {
+            if (fixed)
+                for (int64_t i = 0; i <= nreq; i++) dst_offsets[i] = i * (fixed_count > 0 ? fixed_count * R : 0);
+            else
+                CU(cudaMemcpyAsync(dst_offsets, s->scr.req_dst, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    if (total_bytes) *total_bytes = fixed ? upper : (int64_t)s->h_status[1];
+    return decode_status(s->h_status[0], bad_index);
+}
+
+// completes a batch issued with DDS_NO_SYNC
+int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    if (!s->pending) return DDS_OK;
+    s->pending = false;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->pending_stream));
+    if (total_bytes) *total_bytes = s->pending_fixed_total >= 0 ? s->pending_fixed_total : (int64_t)s->h_status[1];
+    return decode_status(s->h_status[0], bad_index);
+}
+
+int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int itemsize, void *buffer,
+            int buffer_on_device) {
+    // one request through the batch path: same kernel, same checks (ddstore.hpp:197-238)
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) {
+        clear_error();
+        return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    }
+    int64_t cap = count > 0 ? count * v->kv.row_bytes : 0;
+    return dds_get_batch(s, name, &start, nullptr, count, 1, itemsize, buffer, cap, nullptr,
+                         buffer_on_device ? DDS_DST_ON_DEVICE : 0u, nullptr, nullptr, nullptr);
+}
+
+int dds_query(dds_store_t *s, const char *name, dds_varinfo_t *out) {
+    clear_error();
+    if (!s || !out) return fail(DDS_ERR_ARG, "null store or out");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    memset(out, 0, sizeof(*out));
+    out->itemsize = v->itemsize;
+    out->disp = v->disp;
+    out->nranks = s->size;
+    out->fence_active = v->fence_active;
+    out->local_nrows = v->nrows;
+    out->total_nrows = v->lenlist.empty() ? 0 : v->lenlist.back();
+    for (int r = 0; r < s->size && r < 64; r++) out->lenlist[r] = v->lenlist[(size_t)r];
+    out->local_base = v->base;
+    return DDS_OK;
+}
+
+int dds_epoch_begin(dds_store_t *s) {
+    // src/ddstore.cxx:51-63
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    for (auto &x : s->vars)
+        if (x.second.fence_active) return fail(DDS_ERR_FENCE_ACTIVE);
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (int rc = dds_comm_barrier(s->comm)) return rc;
+    for (auto &x : s->vars) x.second.fence_active = true;
+    return DDS_OK;
+}
+
+int dds_epoch_end(dds_store_t *s) {
+    // src/ddstore.cxx:65-77
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    for (auto &x : s->vars)
+        if (!x.second.fence_active) return fail(DDS_ERR_FENCE_INACTIVE);
+    CU(cudaSetDevice(s->device));
+    if (s->pending) dds_batch_wait(s, nullptr, nullptr);
+    CU(cudaStreamSynchronize(s->stream));
+    if (int rc = dds_comm_barrier(s->comm)) return rc;
+    for (auto &x : s->vars) x.second.fence_active = false;
+    return DDS_OK;
+}
+
+static void local_release(dds_store *s) {
+    for (auto &x : s->vars) release_var(x.second, s->rank);
+}
+
+int dds_free(dds_store_t *s) {
+    // src/ddstore.cxx:79-96 (MPI_Win_free is collective; so is this)
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    if (s->vars.empty() && s->zombies.empty()) return DDS_OK;
+    CU(cudaSetDevice(s->device));
+    if (s->pending) dds_batch_wait(s, nullptr, nullptr);
+    CU(cudaDeviceSynchronize());
+    int rc = dds_comm_barrier(s->comm); // nobody is reading any more
+    local_release(s);
+    int rc2 = dds_comm_barrier(s->comm); // every mapping is closed before the memory goes away
+    for (auto &x : s->vars)
+        if (x.second.base) cudaFree(x.second.base);
+    for (void *z : s->zombies) cudaFree(z);
+    s->vars.clear();
+    s->zombies.clear();
+    return rc ? rc : rc2;
+}
+
+void dds_destroy(dds_store_t *s) {
+    if (!s) return;
+    // non-collective local teardown (the collective one is dds_free)
+    if (cudaSetDevice(s->device) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        local_release(s);
+        for (auto &x : s->vars)
+            if (x.second.base) cudaFree(x.second.base);
+        for (void *z : s->zombies) cudaFree(z);
+        if (s->scr.status) cudaFree(s->scr.status);
+        if (s->scr.counters) cudaFree(s->scr.counters);
+        if (s->scr.req_src) cudaFree(s->scr.req_src);
+        if (s->scr.req_dst) cudaFree(s->scr.req_dst);
+        if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
+        if (s->d_starts) cudaFree(s->d_starts);
+        if (s->d_counts) cudaFree(s->d_counts);
+        if (s->d_out) cudaFree(s->d_out);
+        if (s->h_status) cudaFreeHost(s->h_status);
+        if (s->stream) cudaStreamDestroy(s->stream);
+    }
+    (void)cudaGetLastError();
+    delete s;
+}
+
+int dds_synth_fill(dds_store_t *s, const char *name, uint64_t seed) {
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    CU(cudaSetDevice(s->device));
+    int64_t first = s->rank > 0 ? v->lenlist[(size_t)s->rank - 1] : 0;
+    if (ddsk_synth_fill(v->base, first, v->nrows, v->disp, v->itemsize, seed, s->stream))
+        return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    CU(cudaStreamSynchronize(s->stream));
+    return DDS_OK;
+}
+
+unsigned long long dds_kernel_launches(void) { return ddsk_launch_count(); }
+void dds_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes) {
+    ddsk_gather_geometry(ctas, warps_per_cta, stages, chunk_bytes, smem_bytes);
+}
+
+} // extern "C"

@@ -1,0 +1,185 @@
+"""ddstore_b200/store.py -- `PyDDStore`: the reference's Python surface over the C-ABI.
+
+Mirrors /root/reference/src/pyddstore.pyx:58-131 method for method (same names, argument order and
+meaning, same exception types/texts): add / get / epoch_begin / epoch_end / free / init / update, plus
+`get_batch`, the batched form of get() that is this package's hot path. Arrays may be NumPy arrays
+(host) or CUDA tensors / __cuda_array_interface__ objects (device; fetched bytes then never leave HBM).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .comm import as_dds_comm
+
+# dtypes the reference's if-chains accept (src/pyddstore.pyx:69-80, 88-99, 118-129)
+_NP_OK = {np.dtype(np.int32), np.dtype(np.int64), np.dtype(np.uint8), np.dtype(np.float32),
+          np.dtype(np.float64), np.dtype(np.bool_)}
+_TORCH_OK = {"torch.int32", "torch.int64", "torch.uint8", "torch.float32", "torch.float64", "torch.bool"}
+
+
+class _Buf:
+    """pointer / shape / itemsize / residency of an ndarray, a CUDA tensor or a CAI object"""
+
+    def __init__(self, arr, writable=False):
+        self.keep = arr
+        if isinstance(arr, np.ndarray):
+            assert arr.flags.c_contiguous  # src/pyddstore.pyx:66,85,116
+            if arr.dtype not in _NP_OK:
+                raise NotImplementedError
+            self.ptr, self.on_device = arr.ctypes.data, 0
+            self.shape, self.itemsize, self.size = arr.shape, arr.dtype.itemsize, arr.size
+        elif hasattr(arr, "data_ptr") and hasattr(arr, "element_size"):  # torch.Tensor
+            assert arr.is_contiguous()
+            if str(arr.dtype) not in _TORCH_OK:
+                raise NotImplementedError
+            self.ptr, self.on_device = arr.data_ptr(), 1 if arr.is_cuda else 0
+            self.shape, self.itemsize, self.size = tuple(arr.shape), arr.element_size(), arr.numel()
+        elif hasattr(arr, "__cuda_array_interface__"):
+            cai = arr.__cuda_array_interface__
+            if cai.get("strides") is not None:
+                raise ValueError("device array must be C-contiguous")
+            dt = np.dtype(cai["typestr"])
+            if dt not in _NP_OK:
+                raise NotImplementedError
+            self.ptr, self.on_device = cai["data"][0], 1
+            self.shape, self.itemsize = tuple(cai["shape"]), dt.itemsize
+            self.size = int(np.prod(self.shape, dtype=np.int64))
+        else:
+            raise TypeError(f"unsupported array type {type(arr).__name__}")
+        self.nbytes = self.size * self.itemsize
+
+
+def _i64(x):
+    """host int64 contiguous ndarray view of an index list/array"""
+    return np.ascontiguousarray(x, dtype=np.int64)
+
+
+class PyDDStore:
+    def __init__(self, comm=None, method=0, device=None):
+        # src/pyddstore.pyx:61-63. `comm`: see ddstore_b200.comm.as_dds_comm; `device`: CUDA ordinal
+        # for this rank's shards (default: the current device).
+        self._L = _capi.lib()
+        self._comm = as_dds_comm(comm)
+        self._h = self._L.dds_create(self._comm.handle, -1 if device is None else int(device), int(method))
+        if not self._h:
+            raise RuntimeError(_capi.last_error())
+        self.rank, self.size = self._L.dds_rank(self._h), self._L.dds_size(self._h)
+        self._itemsize = {}  # per-variable itemsize, cached for the hot path
+        self.last_bad_index = -1
+
+    # ---------------------------------------------------------------- reference surface
+    def add(self, name, arr):
+        # src/pyddstore.pyx:65-82
+        b = _Buf(arr)
+        nrows = b.shape[0]
+        disp = b.size // b.shape[0] if b.shape[0] else int(np.prod(b.shape[1:], dtype=np.int64))
+        _capi.raise_for(self._L.dds_add(self._h, name.encode(), b.ptr, nrows, disp, b.itemsize, b.on_device))
+
+    def get(self, name, arr, start=0):
+        # src/pyddstore.pyx:84-101: count = arr.shape[0]; fills arr in place
+        b = _Buf(arr, writable=True)
+        count = b.shape[0]
+        _capi.raise_for(self._L.dds_get(self._h, name.encode(), int(start), count, b.itemsize, b.ptr, b.on_device))
+
+    def epoch_begin(self):
+        _capi.raise_for(self._L.dds_epoch_begin(self._h))  # src/pyddstore.pyx:103-104
+
+    def epoch_end(self):
+        _capi.raise_for(self._L.dds_epoch_end(self._h))  # src/pyddstore.pyx:106-107
+
+    def free(self):
+        if self._h:
+            self._itemsize.clear()
+            _capi.raise_for(self._L.dds_free(self._h))  # src/pyddstore.pyx:109-110
+
+    def init(self, name, nrows, disp, itemsize=1):
+        _capi.raise_for(self._L.dds_init(self._h, name.encode(), int(nrows), int(disp), int(itemsize)))  # :112-113
+
+    def update(self, name, arr, offset):
+        # src/pyddstore.pyx:115-131
+        b = _Buf(arr)
+        _capi.raise_for(self._L.dds_update(self._h, name.encode(), b.ptr, b.shape[0], int(offset), b.itemsize,
+                                           b.on_device))
+
+    # ---------------------------------------------------------------- the batched hot path
+    def get_batch(self, name, starts, counts=None, out=None, count=None, offsets=None, stream=None, wait=True):
+        """Fetch len(starts) requests in ONE kernel launch, packed back to back in request order.
+
+        starts/counts: int64 index arrays (host ndarray/list, or CUDA int64 tensors). counts=None means
+        every request fetches `count` rows (default 1): the fixed-stride fast path.
+        out: destination (host ndarray or CUDA tensor) of at least the packed size; row layout is the
+        caller's business exactly as with get() (src/pyddstore.pyx:84-87 never checks it either).
+        offsets: optional int64 array of len(starts)+1 receiving the byte offset of every request
+        (same residency as `out`). Returns the number of packed bytes.
+        wait=False (device indices + device out only): enqueue on `stream` and return at once; call
+        `wait()` later for the status. Several such batches may be queued on one stream.
+        Raises the reference's ValueError for the first invalid request (requests before it are delivered).
+        """
+        itemsize = self._itemsize.get(name)
+        if itemsize is None:
+            itemsize = self._itemsize[name] = self.query(name)["itemsize"]
+        if out is None:
+            raise ValueError("get_batch needs an `out` buffer (like get(), it never allocates)")
+        ob = _Buf(out, writable=True)
+        s_dev = hasattr(starts, "data_ptr") and getattr(starts, "is_cuda", False)
+        if s_dev:
+            nreq = starts.numel()
+            sp = starts.data_ptr()
+            cp = counts.data_ptr() if counts is not None else None
+            keep = (starts, counts)
+        else:
+            sa = _i64(starts)
+            nreq = sa.size
+            sp = sa.ctypes.data
+            ca = _i64(counts) if counts is not None else None
+            cp = ca.ctypes.data if ca is not None else None
+            keep = (sa, ca)
+        flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | (_capi.DST_ON_DEVICE if ob.on_device else 0)
+        if not wait:
+            flags |= _capi.NO_SYNC
+        op = None
+        if offsets is not None:
+            fb = _Buf(offsets, writable=True)
+            if fb.on_device != ob.on_device or fb.itemsize != 8 or fb.size < nreq + 1:
+                raise ValueError("offsets must be int64[len(starts)+1] with the same residency as out")
+            op = fb.ptr
+        total, bad = C.c_int64(0), C.c_int64(-1)
+        rc = self._L.dds_get_batch(self._h, name.encode(), sp, cp, 1 if count is None else int(count), nreq,
+                                   itemsize, ob.ptr, ob.nbytes, op, flags,
+                                   None if stream is None else C.c_void_p(int(stream)), C.byref(total), C.byref(bad))
+        del keep
+        self.last_bad_index = bad.value
+        _capi.raise_for(rc)
+        return total.value
+
+    def wait(self):
+        """complete the batches queued with wait=False; raises like get_batch; returns packed bytes of the last"""
+        total, bad = C.c_int64(0), C.c_int64(-1)
+        rc = self._L.dds_batch_wait(self._h, C.byref(total), C.byref(bad))
+        self.last_bad_index = bad.value
+        _capi.raise_for(rc)
+        return total.value
+
+    # ---------------------------------------------------------------- extras
+    def query(self, name):
+        vi = _capi.VarInfo()
+        _capi.raise_for(self._L.dds_query(self._h, name.encode(), C.byref(vi)))
+        return {"itemsize": vi.itemsize, "disp": vi.disp, "nranks": vi.nranks, "fence_active": bool(vi.fence_active),
+                "local_nrows": vi.local_nrows, "total_nrows": vi.total_nrows,
+                "lenlist": [vi.lenlist[i] for i in range(vi.nranks)], "local_base": vi.local_base}
+
+    def synth_fill(self, name, seed):
+        _capi.raise_for(self._L.dds_synth_fill(self._h, name.encode(), int(seed)))
+
+    def close(self):
+        """non-collective teardown of this rank's handle (the collective one is free())"""
+        if self._h:
+            self._L.dds_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

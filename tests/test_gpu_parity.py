@@ -1,0 +1,378 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI (ddstore_b200._capi via PyDDStore),
+against the oracle and the committed golden vectors. Bit-exact: every comparison is on raw bytes."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.gpu_helpers import packed_nbytes, run_world
+from tests.helpers import golden_world_shards, load_golden, random_valid_requests, random_world, sha
+
+pytestmark = pytest.mark.gpu
+G = load_golden()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+# ------------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("w", G["worlds"], ids=[w["name"] for w in G["worlds"]])
+def test_golden_worlds(w):
+    P = len(w["nrows"])
+    shards = golden_world_shards(w)
+    dtype = np.dtype(w["dtype"])
+    row = w["disp"] * dtype.itemsize
+
+    def body(store, r):
+        store.add("v", shards[r])
+        q = store.query("v")
+        assert q["lenlist"] == w["lenlist"] and q["disp"] == w["disp"] and q["itemsize"] == w["itemsize"]
+        if r != w["rank"]:
+            return None
+        good = []
+        for req in w["requests"]:
+            buf = np.zeros((req["count"], w["disp"]), dtype)
+            if "error" in req:
+                with pytest.raises(ValueError) as ei:
+                    store.get("v", buf, req["start"])
+                assert str(ei.value) == req["error"]
+            else:
+                store.get("v", buf, req["start"])
+                assert sha(buf.tobytes()) == req["sha256"]
+                if "hex" in req:
+                    assert buf.tobytes().hex() == req["hex"]
+                good.append((req["start"], req["count"]))
+        st, ct = [g[0] for g in good], [g[1] for g in good]
+        out = np.zeros(w["batch_nbytes"], np.uint8)
+        offs = np.zeros(len(st) + 1, np.int64)
+        n = store.get_batch("v", st, ct, out=out, offsets=offs)
+        assert n == w["batch_nbytes"] and sha(out.tobytes()) == w["batch_sha256"]
+        assert offs.tolist() == np.concatenate([[0], np.cumsum(np.array(ct) * row)]).tolist()
+        # the whole request list incl. the invalid ones: first bad index + the reference's text
+        st = [r_["start"] for r_ in w["requests"]]
+        ct = [r_["count"] for r_ in w["requests"]]
+        first_bad = next((i for i, r_ in enumerate(w["requests"]) if "error" in r_), None)
+        if first_bad is not None:
+            out2 = np.zeros(max(packed_nbytes(ct, row), 16), np.uint8)
+            with pytest.raises(ValueError) as ei:
+                store.get_batch("v", st, ct, out=out2)
+            assert str(ei.value) == w["requests"][first_bad]["error"] and store.last_bad_index == first_bad
+            # requests before the first bad one were delivered, like the serial loop
+            pre = packed_nbytes(ct[:first_bad], row)
+            exp, _, _, _ = O.np_get_batch(shards, st[:first_bad], ct[:first_bad])
+            assert out2[:pre].tobytes() == exp.tobytes()
+        return True
+
+    res = run_world(P, body)
+    assert res[w["rank"]] is True
+
+
+def test_demo_cxx_known_answer():
+    # test/demo.cxx:20-37 at P=2
+    def body(store, r):
+        buffer = np.array([1, 2, 3, 4], np.float64).reshape(2, 2) + 10 * r
+        store.add("var", buffer)
+        getbuf = np.zeros((1, 2), np.float64)
+        start = (2 * (r + 1)) % (2 * 2) + 1
+        store.get("var", getbuf, start)
+        return getbuf.reshape(-1).tolist()
+
+    assert run_world(2, body) == [[13.0, 14.0], [3.0, 4.0]]
+    assert [d["got"] for d in G["demo_cxx"]] == [[13.0, 14.0], [3.0, 4.0]]
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+def test_demo_py_mean_property(dt):
+    # test/demo.py:35-56 / test/test.py:144-159: shard r is all (r+1); mean(row idx) == idx//num + 1
+    rec = G["demo_py"][dt]
+    num, dim = rec["num"], rec["dim"]
+
+    def body(store, r):
+        store.add("var", np.ones((num, dim), dt) * (r + 1))
+        means = []
+        for idx in rec["idx"]:
+            buff = np.zeros((1, dim), dt)
+            store.epoch_begin()
+            store.get("var", buff, idx)
+            store.epoch_end()
+            means.append(float(np.mean(buff)))
+        return means
+
+    for means in run_world(rec["P"], body):
+        assert means == rec["means"] == [i // num + 1 for i in rec["idx"]]
+
+
+# ------------------------------------------------------------------------------- random worlds vs the oracle
+CASES = [(np.float32, 1, 4), (np.float32, 16, 8), (np.int64, 2, 3), (np.uint8, 7, 2), (np.float64, 5, 1),
+         (np.int32, 3, 5), (np.bool_, 3, 2), (np.uint8, 1, 4), (np.float32, 1024, 2)]
+
+
+@pytest.mark.parametrize("dtype,disp,P", CASES)
+def test_random_worlds_vs_oracle(coracle, dtype, disp, P):
+    torch = _torch()
+    rng = np.random.default_rng(4242 + disp * 7 + P)
+    nrows, shards = random_world(rng, P, dtype, disp, max_rows=400)
+    ll = O.np_lenlist(nrows)
+    row = disp * np.dtype(dtype).itemsize
+    starts, counts = random_valid_requests(rng, ll, 777, max_count=64)
+    exp, exp_offs, bad, rc = coracle.get_batch(shards, starts, counts)
+    assert bad == -1
+    fixed_starts = starts[counts >= 3][:300]
+    exp_fixed3 = None
+    ok3 = [s for s in fixed_starts.tolist() if coracle.locate(ll, s, 3)[2] == 0]
+    if ok3:
+        exp_fixed3, _, bad, _ = coracle.get_batch(shards, ok3, [3] * len(ok3))
+        assert bad == -1
+
+    def body(store, r):
+        store.add("v", shards[r])
+        # (a) variable counts, host indices -> host buffer, with offsets
+        out = np.zeros(max(exp.size, 1), np.uint8)
+        offs = np.zeros(len(starts) + 1, np.int64)
+        n = store.get_batch("v", starts, counts, out=out, offsets=offs)
+        assert n == exp.size and out[:n].tobytes() == exp.tobytes() and offs.tolist() == exp_offs.tolist()
+        # (b) device indices -> device buffer (bytes never leave HBM), device offsets
+        dev = torch.device("cuda", 0)
+        d_out = torch.zeros(max(exp.size, 16) + 64, dtype=torch.uint8, device=dev)
+        d_offs = torch.zeros(len(starts) + 1, dtype=torch.int64, device=dev)
+        n = store.get_batch("v", torch.from_numpy(starts).to(dev), torch.from_numpy(counts).to(dev), out=d_out,
+                            offsets=d_offs)
+        assert n == exp.size and d_out[:n].cpu().numpy().tobytes() == exp.tobytes()
+        assert d_offs.cpu().numpy().tolist() == exp_offs.tolist()
+        assert int(d_out[n:].sum()) == 0  # nothing written past the packed end
+        # (c) fixed count (the single-launch path), host and device destinations
+        if ok3:
+            out3 = np.zeros(exp_fixed3.size, np.uint8)
+            n3 = store.get_batch("v", ok3, out=out3, count=3)
+            assert n3 == exp_fixed3.size and out3.tobytes() == exp_fixed3.tobytes()
+            d3 = torch.zeros(exp_fixed3.size, dtype=torch.uint8, device=dev)
+            store.get_batch("v", ok3, out=d3, count=3)
+            assert d3.cpu().numpy().tobytes() == exp_fixed3.tobytes()
+        # (d) per-request get() == the reference's per-sample loop
+        for s, c in list(zip(starts.tolist(), counts.tolist()))[:40]:
+            buf = np.zeros((c, disp), dtype)
+            store.get("v", buf, s)
+            e, _, _, _ = coracle.get_batch(shards, [s], [c])
+            assert buf.tobytes() == e.tobytes()
+        return True
+
+    assert all(run_world(P, body))
+
+
+def test_every_alignment_phase(coracle):
+    """uint8 rows of odd width: source and destination 16-byte phases sweep all 16 x 16 combinations, and
+    request sizes straddle the head/body/tail cases of the drain (1..70 bytes and a few multi-chunk ones)."""
+    rng = np.random.default_rng(99)
+    disp = 1
+    shard = rng.integers(0, 256, size=(300000, disp), dtype=np.uint8)
+    starts, counts = [], []
+    for src_phase in range(16):
+        for n in list(range(1, 40)) + [63, 64, 65, 70, 4095, 4096, 4097, 9000]:
+            starts.append(1024 + src_phase + 16 * int(rng.integers(0, 1000)))
+            counts.append(n)
+    perm = rng.permutation(len(starts))
+    starts, counts = np.array(starts, np.int64)[perm], np.array(counts, np.int64)[perm]
+    exp, exp_offs, bad, _ = coracle.get_batch([shard], starts, counts)
+    assert bad == -1
+
+    def body(store, r):
+        store.add("b", shard)
+        out = np.zeros(exp.size, np.uint8)
+        n = store.get_batch("b", starts, counts, out=out)
+        assert n == exp.size
+        if out.tobytes() != exp.tobytes():
+            badpos = int(np.nonzero(out != exp)[0][0])
+            req = int(np.searchsorted(exp_offs, badpos, side="right") - 1)
+            raise AssertionError(f"first mismatch at byte {badpos} (request {req}: start={starts[req]} count={counts[req]} "
+                                 f"dst_off={exp_offs[req]})")
+        return True
+
+    assert all(run_world(1, body))
+
+
+def test_variable_length_cfg3_shape(coracle):
+    """config 3 at reduced size: disp=1 float32 samples of 100..10000 elements, 4 ranks."""
+    rng = np.random.default_rng(42)
+    P, nsamp = 4, 2000
+    L = rng.integers(100, 10001, size=nsamp)
+    sample_start = np.concatenate([[0], np.cumsum(L)])
+    per = nsamp // P
+    shards = []
+    for r in range(P):
+        n = int(sample_start[(r + 1) * per] - sample_start[r * per])
+        shards.append(rng.integers(0, 2**32, size=(n, 1), dtype=np.uint32).view(np.float32))
+    pick = rng.integers(0, nsamp, size=1500)
+    starts, counts = sample_start[pick], L[pick]
+    exp, exp_offs, bad, _ = coracle.get_batch(shards, starts, counts)
+    assert bad == -1
+
+    def body(store, r):
+        store.add("x", shards[r])
+        out = np.zeros(exp.size, np.uint8)
+        assert store.get_batch("x", starts, counts, out=out) == exp.size
+        assert out.tobytes() == exp.tobytes()
+        return True
+
+    assert all(run_world(P, body))
+
+
+def test_multi_array_cfg4_shape(coracle):
+    """config 4 at reduced size: node_feat float32 [n_i,16] + edge_index int64 [8 n_i, 2], 2 ranks."""
+    rng = np.random.default_rng(4)
+    P, nsamp = 2, 600
+    n = rng.integers(8, 513, size=nsamp)
+    e = 8 * n
+    ns, es = np.concatenate([[0], np.cumsum(n)]), np.concatenate([[0], np.cumsum(e)])
+    per = nsamp // P
+    feat = [rng.integers(0, 2**32, size=(int(ns[(r + 1) * per] - ns[r * per]), 16), dtype=np.uint32).view(np.float32)
+            for r in range(P)]
+    edge = [rng.integers(-2**40, 2**40, size=(int(es[(r + 1) * per] - es[r * per]), 2), dtype=np.int64) for r in range(P)]
+    pick = rng.integers(0, nsamp, size=500)
+    ef, _, b1, _ = coracle.get_batch(feat, ns[pick], n[pick])
+    ee, _, b2, _ = coracle.get_batch(edge, es[pick], e[pick])
+    assert b1 == b2 == -1
+
+    def body(store, r):
+        store.add("node_feat", feat[r])
+        store.add("edge_index", edge[r])
+        of, oe = np.zeros(ef.size, np.uint8), np.zeros(ee.size, np.uint8)
+        store.get_batch("node_feat", ns[pick], n[pick], out=of)
+        store.get_batch("edge_index", es[pick], e[pick], out=oe)
+        assert of.tobytes() == ef.tobytes() and oe.tobytes() == ee.tobytes()
+        return True
+
+    assert all(run_world(P, body))
+
+
+def test_large_requests_multi_chunk_and_segments(coracle):
+    """a few multi-megabyte requests (config 5 shape) so one request spans many chunks and segments"""
+    rng = np.random.default_rng(11)
+    disp = 256 * 1024  # 1 MiB rows of float32
+    shards = [rng.integers(0, 2**32, size=(6, disp), dtype=np.uint32).view(np.float32) for _ in range(2)]
+    starts = np.array([7, 0, 11, 3, 6, 5], np.int64)
+    counts = np.array([1, 3, 1, 2, 4, 1], np.int64)
+    exp, _, bad, _ = coracle.get_batch(shards, starts, counts)
+    assert bad == -1
+
+    def body(store, r):
+        store.add("big", shards[r])
+        out = np.zeros(exp.size, np.uint8)
+        assert store.get_batch("big", starts, counts, out=out) == exp.size
+        assert out.tobytes() == exp.tobytes()
+        return True
+
+    assert all(run_world(2, body))
+
+
+# ------------------------------------------------------------------------------- init / update / fences / errors
+def test_init_update_and_fence_state_machine():
+    def body(store, r):
+        nrows = [4, 0, 6][r]
+        store.init("z", nrows, 3, 4)  # include/ddstore.hpp:110-179
+        if r == 0:
+            store.update("z", np.arange(6, dtype=np.float32).reshape(2, 3), 1)  # :181-195
+            with pytest.raises(ValueError, match="Invalid data type"):
+                store.update("z", np.zeros((1, 3), np.float64), 0)
+        store.epoch_begin()
+        with pytest.raises(RuntimeError, match="Fence already activated"):  # src/ddstore.cxx:57-58
+            store.epoch_begin()
+        got = np.full((4, 3), -1, np.float32)
+        store.get("z", got, 0)
+        store.epoch_end()
+        with pytest.raises(RuntimeError, match="Fence is not activated"):  # src/ddstore.cxx:71-72
+            store.epoch_end()
+        exp = np.zeros((4, 3), np.float32)
+        exp[1:3] = np.arange(6, dtype=np.float32).reshape(2, 3)
+        assert got.tobytes() == exp.tobytes()
+        with pytest.raises(ValueError, match="Invalid data type"):  # include/ddstore.hpp:202-203
+            store.get("z", np.zeros((1, 3), np.float64), 0)
+        with pytest.raises(KeyError):
+            store.get("nope", np.zeros((1, 3), np.float32), 0)
+        with pytest.raises(NotImplementedError):  # src/pyddstore.pyx:100-101
+            store.get("z", np.zeros((1, 3), np.float16), 0)
+        return True
+
+    assert all(run_world(3, body))
+
+
+def test_invalid_disp_on_the_differing_rank():
+    def body(store, r):
+        arr = np.zeros((2, 4 if r != 1 else 3), np.float32)
+        if r == 1:
+            with pytest.raises(ValueError, match="Invalid disp"):  # include/ddstore.hpp:81-82
+                store.add("bad", arr)
+        else:
+            store.add("bad", arr)
+        return True
+
+    assert all(run_world(3, body))
+
+
+def test_capacity_is_enforced_without_overrun():
+    torch = _torch()
+
+    def body(store, r):
+        store.add("v", np.arange(64 * 8, dtype=np.float32).reshape(64, 8))
+        d = torch.full((100,), 7, dtype=torch.uint8, device="cuda:0")
+        with pytest.raises(ValueError, match="too small"):
+            store.get_batch("v", [0, 1, 2, 3], out=d[:96], count=1)  # needs 128 bytes
+        assert int((d != 7).sum()) == 0
+        return True
+
+    assert all(run_world(1, body))
+
+
+# ------------------------------------------------------------------------------- synthetic payload + full size
+def test_synth_fill_matches_oracle_generator(coracle):
+    def body(store, r):
+        for name, dt, disp, seed in (("f", np.float32, 33, 0xDD5), ("i", np.int64, 2, 0xDD6), ("b", np.uint8, 5, 0xDD7)):
+            nrows = 1000 + 13 * r
+            store.init(name, nrows, disp, np.dtype(dt).itemsize)
+            store.synth_fill(name, seed)
+            ll = store.query(name)["lenlist"]
+            first = ll[r - 1] if r else 0
+            got = np.zeros((nrows, disp), dt)
+            store.get(name, got, first)
+            assert got.tobytes() == coracle.synth_rows(seed, first, nrows, disp, dt).tobytes()
+        return True
+
+    assert all(run_world(2, body))
+
+
+def test_full_size_config2_spot_check(coracle):
+    """BASELINE config 2 at FULL size on one GPU: 10M x 1024 float32 (40.96 GB), uniform-random batch of
+    65536 rows. Expected bytes are recomputed from the generator for the sampled rows (size-independent
+    property: every fetched row equals synth(row index))."""
+    torch = _torch()
+    free, total = torch.cuda.mem_get_info(0)
+    nrows, disp = 10_000_000, 1024
+    if free < nrows * disp * 4 + (2 << 30):
+        pytest.skip("not enough free HBM for the full-size shard")
+    B = 65536
+
+    def body(store, r):
+        store.init("x", nrows, disp, 4)
+        store.synth_fill("x", 0xDD5)
+        rng = np.random.default_rng(1234)
+        idx = rng.integers(0, nrows, size=B)
+        d_out = torch.empty(B * disp, dtype=torch.float32, device="cuda:0")
+        n = store.get_batch("x", idx, out=d_out, count=1)
+        assert n == B * disp * 4
+        got = d_out.cpu().numpy().reshape(B, disp)
+        sample = rng.choice(B, size=2048, replace=False)
+        for j in sample.tolist() + [0, B - 1]:
+            exp = O.np_synth_rows(0xDD5, int(idx[j]), 1, disp, np.float32)
+            assert got[j].tobytes() == exp.tobytes(), f"row {j} (sample {idx[j]})"
+        # checksum-of-checksums over the whole batch against a vectorised recomputation
+        blk = 8192
+        for b0 in range(0, B, blk):
+            g = (idx[b0:b0 + blk].astype(np.uint64)[:, None] * np.uint64(disp) + np.arange(disp, dtype=np.uint64)[None, :])
+            x = (g ^ np.uint64(0xDD5)) + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            x = (x ^ (x >> np.uint64(31))).astype(np.uint32)
+            assert np.array_equal(x, got[b0:b0 + blk].view(np.uint32))
+        return True
+
+    assert all(run_world(1, body, timeout=900))
