@@ -133,12 +133,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------- reference arm
 def cpu_reference_run(cpu_samples, cpu_batch, steps, warmup):
     """The reference's own get() path on the host cores: the UNMODIFIED DDStore (method 0) compiled against the
-    MPI thread-rank shim when oracle/_ref is built, else the oracle's C port. One rank-thread per core (<= 32),
+    MPI thread-rank shim when oracle/_ref is built, else the oracle's C port. One rank-thread per core,
     each doing `cpu_batch` blocking single-row get() calls per step into a packed host buffer -- the loader loop
     of examples/vae/distdataset.py:79-89. Returns (GB/s aggregate, info dict)."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    P = max(1, min(32, cores))
+    P = max(1, min(256, cores))  # every host core gets a rank-thread
     per = cpu_samples // P
     co = O.COracle()
     shards = [co.synth_rows(SEED, r * per, per, DISP, np.float32) for r in range(P)]
@@ -247,7 +247,10 @@ def run_ours(args):
     idx_dev = [t.to(dev) for t in idx_host]
     out_dev = torch.empty(B * ROW_BYTES, dtype=torch.uint8, device=dev)
     step_bytes = B * ROW_BYTES
-    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)  # the launching stream: kernels AND the timing events live on it
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
 
     def barrier():
         if N > 1:

@@ -127,6 +127,7 @@ struct dds_store {
     bool pending = false;
     cudaStream_t pending_stream = nullptr;
     int64_t pending_fixed_total = -1;
+    int64_t pending_nreq = 0;
 };
 
 namespace {
@@ -302,7 +303,7 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     return dds_comm_barrier(s->comm);
 }
 
-int decode_status(unsigned long long st, int64_t *bad_index) {
+int decode_status_word(unsigned long long st, int64_t *bad_index) {
     if (st == DDSK_STATUS_OK) {
         if (bad_index) *bad_index = -1;
         return DDS_OK;
@@ -317,6 +318,15 @@ int decode_status(unsigned long long st, int64_t *bad_index) {
         return fail(DDS_ERR_CAPACITY);
     default: return fail(DDS_ERR_WATCHDOG);
     }
+}
+
+// The device status word is sticky (kernels only atomicMin into it): re-arm it after an error was read.
+int decode_status(dds_store *s, cudaStream_t stream, unsigned long long st, int64_t *bad_index) {
+    if (st != DDSK_STATUS_OK) {
+        cudaMemsetAsync(s->scr.status, 0xFF, 8, stream);
+        cudaStreamSynchronize(stream);
+    }
+    return decode_status_word(st, bad_index);
 }
 
 } // namespace
@@ -403,6 +413,7 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
               cudaMalloc((void **)&s->scr.status, 8) == cudaSuccess &&
               cudaMalloc((void **)&s->scr.counters, 16) == cudaSuccess &&
               cudaMemset(s->scr.counters, 0, 16) == cudaSuccess &&
+              cudaMemset(s->scr.status, 0xFF, 8) == cudaSuccess &&
               cudaMallocHost((void **)&s->h_status, 16) == cudaSuccess;
     if (!ok) {
         cuda_fail(cudaGetLastError(), "dds_create: device setup");
@@ -521,20 +532,20 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
     int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
     int krc;
     if (fixed)
-        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, !chain, st);
+        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
     else
-        krc = ddsk_gather_var(&v->kv, d_starts, d_counts, nreq, d_dst, cap, d_offsets, &s->scr, !chain, st);
+        krc = ddsk_gather_var(&v->kv, d_starts, d_counts, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
-    CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
-    if (!fixed) CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[nreq], 8, cudaMemcpyDeviceToHost, st));
     s->pending_fixed_total = fixed ? upper : -1;
-
-    if (no_sync) {
+    s->pending_nreq = nreq;
+    if (no_sync) { // nothing but the kernel(s) goes on the stream; the status word is read back in dds_batch_wait
         s->pending = true;
         s->pending_stream = st;
         return DDS_OK;
     }
+    CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
+    if (!fixed) CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[nreq], 8, cudaMemcpyDeviceToHost, st));
 
     // ---- results back to a host destination
     if (!dst_dev) {
@@ -555,7 +566,7 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
     }
     CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = fixed ? upper : (int64_t)s->h_status[1];
-    return decode_status(s->h_status[0], bad_index);
+    return decode_status(s, st, s->h_status[0], bad_index);
 }
 
 // completes a batch issued with DDS_NO_SYNC
@@ -564,9 +575,13 @@ int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
     if (!s->pending) return DDS_OK;
     s->pending = false;
     CU(cudaSetDevice(s->device));
-    CU(cudaStreamSynchronize(s->pending_stream));
+    cudaStream_t st = s->pending_stream;
+    CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
+    if (s->pending_fixed_total < 0)
+        CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[s->pending_nreq], 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = s->pending_fixed_total >= 0 ? s->pending_fixed_total : (int64_t)s->h_status[1];
-    return decode_status(s->h_status[0], bad_index);
+    return decode_status(s, st, s->h_status[0], bad_index);
 }
 
 int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int itemsize, void *buffer,

@@ -147,11 +147,21 @@ class PyDDStore:
         total, bad = C.c_int64(0), C.c_int64(-1)
         rc = self._L.dds_get_batch(self._h, name.encode(), sp, cp, 1 if count is None else int(count), nreq,
                                    itemsize, ob.ptr, ob.nbytes, op, flags,
-                                   None if stream is None else C.c_void_p(int(stream)), C.byref(total), C.byref(bad))
+                                   self._stream_arg(stream), C.byref(total), C.byref(bad))
         del keep
         self.last_bad_index = bad.value
         _capi.raise_for(rc)
         return total.value
+
+    @staticmethod
+    def _stream_arg(stream):
+        """None -> the store's own stream; a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)
+        otherwise. Handle 0 is CUDA's legacy default stream, which the C-ABI spells cudaStreamLegacy (0x1)
+        because NULL there means "the store's stream"."""
+        if stream is None:
+            return None
+        h = int(stream)
+        return C.c_void_p(h if h != 0 else 1)
 
     def wait(self):
         """complete the batches queued with wait=False; raises like get_batch; returns packed bytes of the last"""

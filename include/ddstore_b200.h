@@ -122,6 +122,8 @@ int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int 
  * `fixed_count` rows. dst_offsets (nullable) receives nreq+1 byte offsets (exclusive scan).
  * On the first (lowest-index) invalid request returns its DDS_ERR_START/COUNT and its index in
  * *bad_index; requests before it are delivered, like the serial loop that stops at the exception. */
+/* cuda_stream: a cudaStream_t to enqueue on; NULL selects the store's own stream (pass cudaStreamLegacy,
+ * (void*)0x1, for CUDA's legacy default stream). */
 #define DDS_IDX_ON_DEVICE 1u /* starts / counts are device pointers */
 #define DDS_DST_ON_DEVICE 2u /* dst / dst_offsets are device pointers */
 #define DDS_NO_SYNC 4u       /* needs both flags above: enqueue on cuda_stream and return; dds_batch_wait() reports */
