@@ -558,11 +558,13 @@ int pick_geometry() {
 template <bool FIXED, int NW, int S, int CH>
 int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
     constexpr int smem = NW * S * (CH + 32);
-    static bool configured = false;
+    static std::atomic<unsigned long long> configured{0}; // bit d: attribute set on device d (it is per device)
     auto kern = dds_gather_kernel<FIXED, NW, S, CH>;
-    if (!configured) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured.load() & (1ull << dev))) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (dev < 64) configured.fetch_or(1ull << dev);
     }
     int per_sm = g_ctas_per_sm;
     while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@
 #include "ddstore_b200.h"
 #include "internal.h"
 #include "kernels.h"
+#include "vmm.h"
 
 
 namespace {
@@ -91,6 +93,9 @@ struct PeerRec { // what every rank publishes in add()/init(): the reference's A
     int32_t device;
     uint64_t raw_ptr;
     uint64_t host_tag;
+    uint64_t alloc_bytes; // mapped size of the shard block
+    int32_t vmm;          // 1: CUDA VMM block shared by POSIX fd; 0: cudaMalloc + legacy cudaIpc handle
+    int32_t pad_;
     cudaIpcMemHandle_t handle;
 };
 
@@ -102,8 +107,11 @@ struct Var {
     std::vector<int64_t> lenlist;
     void *base = nullptr; // local shard (device)
     size_t bytes = 0;
+    bool vmm = false;               // shard is a CUDA VMM block (else cudaMalloc)
+    dds_vmm::Block block;           // valid when vmm
     std::vector<void *> peer_base;  // as mapped here
-    std::vector<char> peer_opened;  // 1 = cudaIpcOpenMemHandle'd (must be closed)
+    std::vector<char> peer_opened;  // 1 = cudaIpcOpenMemHandle'd (must be closed), 2 = VMM import (peer_block)
+    std::vector<dds_vmm::Block> peer_block;
     bool fence_active = false;
     ddsk_var_t kv;
 };
@@ -116,6 +124,9 @@ struct dds_store {
     cudaStream_t stream = nullptr;
     std::map<std::string, Var> vars;
     std::vector<void *> zombies; // shards of failed add()s, kept until free so no peer mapping dangles
+    std::vector<dds_vmm::Block> zombie_blocks;
+    unsigned long long token = 0; // job-unique tag for the descriptor-passing sockets
+    unsigned long long reg_seq = 0;
     // scratch for the batched path
     ddsk_scratch_t scr;
     int64_t *d_starts = nullptr, *d_counts = nullptr;
@@ -191,10 +202,22 @@ Var *find_var(dds_store *s, const char *name) {
 }
 
 void release_var(Var &v, int rank) {
-    for (size_t r = 0; r < v.peer_base.size(); r++)
-        if ((int)r != rank && v.peer_opened[r] && v.peer_base[r]) cudaIpcCloseMemHandle(v.peer_base[r]);
+    for (size_t r = 0; r < v.peer_base.size(); r++) {
+        if ((int)r == rank || !v.peer_base[r]) continue;
+        if (v.peer_opened[r] == 1) cudaIpcCloseMemHandle(v.peer_base[r]);
+        if (v.peer_opened[r] == 2) dds_vmm::release(&v.peer_block[r]);
+    }
     v.peer_base.clear();
     v.peer_opened.clear();
+    v.peer_block.clear();
+}
+
+void free_shard(Var &v) {
+    if (v.vmm)
+        dds_vmm::release(&v.block);
+    else if (v.base)
+        cudaFree(v.base);
+    v.base = nullptr;
 }
 
 // add() and init() share everything but the fill (ddstore.hpp:39-108 vs :110-179)
@@ -206,12 +229,23 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     if (!zero_fill && !buffer && nrows * (int64_t)disp > 0) return fail(DDS_ERR_ARG, "null buffer");
     CU(cudaSetDevice(s->device));
     const bool exists = s->vars.count(name) != 0;
+    const unsigned long long seq = s->reg_seq++;
 
     // shard: payload + 16 bytes of slack so the kernel's 16-byte-aligned superset loads never leave it
     const size_t payload = (size_t)nrows * (size_t)disp * (size_t)itemsize;
-    const size_t alloc = ((payload + 16 + 255) / 256) * 256;
+    size_t alloc = ((payload + 16 + 255) / 256) * 256;
+    Var v;
+    v.vmm = dds_vmm::available(s->device);
     void *base = nullptr;
-    CU(cudaMalloc(&base, alloc));
+    if (v.vmm) {
+        if (int rc = dds_vmm::alloc(s->device, alloc, &v.block)) return rc;
+        base = v.block.ptr;
+        alloc = v.block.size;
+    } else {
+        CU(cudaMalloc(&base, alloc));
+    }
+    v.base = base;
+    v.bytes = alloc;
     if (zero_fill || payload == 0) {
         CU(cudaMemsetAsync(base, 0, alloc, s->stream));
     } else {
@@ -230,34 +264,38 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     mine.device = s->device;
     mine.raw_ptr = (uint64_t)base;
     mine.host_tag = host_tag();
-    if (s->size > 1) CU(cudaIpcGetMemHandle(&mine.handle, base));
+    mine.alloc_bytes = alloc;
+    mine.vmm = v.vmm ? 1 : 0;
+    if (s->size > 1 && !v.vmm) CU(cudaIpcGetMemHandle(&mine.handle, base));
     std::vector<PeerRec> all((size_t)s->size);
     if (int rc = dds_comm_allgather(s->comm, &mine, all.data(), sizeof(PeerRec))) {
-        cudaFree(base);
+        free_shard(v);
         return rc;
     }
 
     // ddstore.hpp:78-82: every rank must pass the same disp; the ranks that differ from the max throw
     int max_disp = 0;
-    for (auto &p : all) max_disp = std::max(max_disp, (int)p.disp);
-    bool bad_disp = max_disp != disp;
-    bool bad_item = false;
-    for (auto &p : all) bad_item |= p.itemsize != itemsize;
-    if (bad_disp || bad_item || exists) {
-        s->zombies.push_back(base); // peers may have mapped it already; released in dds_free
-        (void)dds_comm_barrier(s->comm); // stay in step with the ranks that succeed
-        if (bad_disp) return fail(DDS_ERR_DISP);
-        if (bad_item) return fail(DDS_ERR_DTYPE);
-        return fail(DDS_ERR_EXISTS, name);
+    bool bad_item = false, mixed = false, other_host = false, other_proc = false;
+    for (auto &p : all) {
+        max_disp = std::max(max_disp, (int)p.disp);
+        bad_item |= p.itemsize != itemsize;
+        mixed |= p.vmm != mine.vmm;
+        other_host |= p.host_tag != mine.host_tag;
+        other_proc |= p.pid != mine.pid;
     }
+    const bool bad_disp = max_disp != disp;
+    int map_rc = DDS_OK;
+    if (mixed) map_rc = fail(DDS_ERR_CUDA, "ranks disagree on the shard allocation mode (set DDS_SHARD_ALLOC on all ranks)");
+    if (other_host)
+        map_rc = fail(DDS_ERR_COMM, "ranks on different hosts: the store spans one NVSwitch box (use one store per box)");
 
-    Var v;
+    // ---- build the "window": every rank's shard mapped here. Done on ALL ranks whatever their own verdict, so
+    // the collective steps stay in lock-step (a rank that will fail below still serves its shard to the others,
+    // like the reference's ranks that pass the disp check keep a window containing every rank's buffer).
     v.name = name;
     v.itemsize = itemsize;
     v.disp = disp;
     v.nrows = nrows;
-    v.base = base;
-    v.bytes = alloc;
     v.lenlist.resize((size_t)s->size);
     int64_t sum = 0; // ddstore.hpp:84-89 inclusive running sum
     for (int r = 0; r < s->size; r++) {
@@ -266,30 +304,86 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     }
     v.peer_base.assign((size_t)s->size, nullptr);
     v.peer_opened.assign((size_t)s->size, 0);
-    for (int r = 0; r < s->size; r++) {
+    v.peer_block.resize((size_t)s->size);
+    std::vector<int> fds;
+    if (!map_rc && v.vmm && other_proc) {
+        std::vector<char> want((size_t)s->size, 0);
+        for (int r = 0; r < s->size; r++) want[(size_t)r] = all[(size_t)r].pid != mine.pid;
+        map_rc = dds_vmm::export_fd(&v.block);
+        char tag[96];
+        snprintf(tag, sizeof(tag), "dds-b200-%016llx-%llu", s->token, seq);
+        // collective even if the export failed (my_fd = -1 would break sendmsg, so send a harmless dup of stdin)
+        int my_fd = v.block.fd >= 0 ? v.block.fd : 0;
+        int xrc = dds_vmm::exchange_fds(s->comm, tag, my_fd, want, &fds);
+        if (!map_rc) map_rc = xrc;
+    }
+    for (int r = 0; r < s->size && !map_rc; r++) {
         const PeerRec &p = all[(size_t)r];
         if (r == s->rank) {
             v.peer_base[(size_t)r] = base;
-        } else if (p.host_tag == mine.host_tag && p.pid == mine.pid) {
+        } else if (p.pid == mine.pid) {
             // thread-ranks of one process: the raw pointer is already valid here
-            if (p.device != s->device) {
+            if (p.device != s->device && !v.vmm) {
                 int can = 0;
                 CU(cudaDeviceCanAccessPeer(&can, s->device, p.device));
-                if (!can) return fail(DDS_ERR_CUDA, "peer GPUs of one process cannot access each other");
+                if (!can) {
+                    map_rc = fail(DDS_ERR_CUDA, "peer GPUs of one process cannot access each other");
+                    break;
+                }
                 cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    map_rc = cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                    break;
+                }
                 (void)cudaGetLastError();
             }
             v.peer_base[(size_t)r] = (void *)p.raw_ptr;
+        } else if (v.vmm) {
+            int fd = fds.size() > (size_t)r ? fds[(size_t)r] : -1;
+            if (fd < 0) {
+                map_rc = fail(DDS_ERR_COMM, "no descriptor received from a peer rank");
+                break;
+            }
+            map_rc = dds_vmm::import_fd(s->device, fd, (size_t)p.alloc_bytes, &v.peer_block[(size_t)r]);
+            close(fd);
+            fds[(size_t)r] = -1;
+            if (map_rc) break;
+            v.peer_base[(size_t)r] = v.peer_block[(size_t)r].ptr;
+            v.peer_opened[(size_t)r] = 2;
         } else {
-            if (p.host_tag != mine.host_tag)
-                return fail(DDS_ERR_COMM, "ranks on different hosts: the store spans one NVSwitch box (use one store per box)");
             void *mapped = nullptr;
             cudaError_t e = cudaIpcOpenMemHandle(&mapped, p.handle, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+            if (e != cudaSuccess) {
+                map_rc = cuda_fail(e, "cudaIpcOpenMemHandle");
+                break;
+            }
             v.peer_base[(size_t)r] = mapped;
             v.peer_opened[(size_t)r] = 1;
         }
+    }
+    for (int fd : fds)
+        if (fd >= 0) close(fd);
+    // VMM blocks are not covered by cudaDeviceEnablePeerAccess: grant the other devices of THIS process access
+    if (!map_rc && v.vmm) {
+        for (int r = 0; r < s->size && !map_rc; r++) {
+            const PeerRec &p = all[(size_t)r];
+            if (r != s->rank && p.pid == mine.pid && p.device != s->device) map_rc = dds_vmm::grant(&v.block, p.device);
+        }
+    }
+    std::string keep_err = dds_last_error();
+    int brc = dds_comm_barrier(s->comm); // every shard is filled, mapped and granted before anyone may read it
+
+    if (map_rc || bad_disp || bad_item || exists) {
+        release_var(v, s->rank);
+        if (v.vmm)
+            s->zombie_blocks.push_back(v.block); // peers may have mapped it; released in dds_free
+        else
+            s->zombies.push_back(base);
+        if (bad_disp) return fail(DDS_ERR_DISP);
+        if (bad_item) return fail(DDS_ERR_DTYPE);
+        if (exists) return fail(DDS_ERR_EXISTS, name);
+        g_err = keep_err;
+        return map_rc;
     }
     memset(&v.kv, 0, sizeof(v.kv));
     for (int r = 0; r < s->size; r++) {
@@ -299,8 +393,7 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     v.kv.row_bytes = (int64_t)disp * (int64_t)itemsize;
     v.kv.nranks = s->size;
     s->vars.emplace(v.name, std::move(v));
-    // every shard is filled and mapped before anyone may read it
-    return dds_comm_barrier(s->comm);
+    return brc;
 }
 
 int decode_status_word(unsigned long long st, int64_t *bad_index) {
@@ -419,6 +512,17 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
         cuda_fail(cudaGetLastError(), "dds_create: device setup");
         delete s;
         return nullptr;
+    }
+    // job-unique token (rank 0's) naming the descriptor-passing sockets of this store
+    {
+        unsigned long long mine = ((unsigned long long)getpid() << 32) ^ (unsigned long long)(uintptr_t)s ^
+                                  (unsigned long long)time(nullptr) * 0x9E3779B97F4A7C15ull;
+        std::vector<unsigned long long> all((size_t)s->size);
+        if (dds_comm_allgather(comm, &mine, all.data(), sizeof(mine)) != DDS_OK) {
+            dds_destroy(s);
+            return nullptr;
+        }
+        s->token = all[0];
     }
     return s;
 }
@@ -650,18 +754,19 @@ int dds_free(dds_store_t *s) {
     // src/ddstore.cxx:79-96 (MPI_Win_free is collective; so is this)
     clear_error();
     if (!s) return fail(DDS_ERR_ARG, "null store");
-    if (s->vars.empty() && s->zombies.empty()) return DDS_OK;
+    if (s->vars.empty() && s->zombies.empty() && s->zombie_blocks.empty()) return DDS_OK;
     CU(cudaSetDevice(s->device));
     if (s->pending) dds_batch_wait(s, nullptr, nullptr);
     CU(cudaDeviceSynchronize());
     int rc = dds_comm_barrier(s->comm); // nobody is reading any more
     local_release(s);
     int rc2 = dds_comm_barrier(s->comm); // every mapping is closed before the memory goes away
-    for (auto &x : s->vars)
-        if (x.second.base) cudaFree(x.second.base);
+    for (auto &x : s->vars) free_shard(x.second);
     for (void *z : s->zombies) cudaFree(z);
+    for (auto &b : s->zombie_blocks) dds_vmm::release(&b);
     s->vars.clear();
     s->zombies.clear();
+    s->zombie_blocks.clear();
     return rc ? rc : rc2;
 }
 
@@ -671,9 +776,9 @@ void dds_destroy(dds_store_t *s) {
     if (cudaSetDevice(s->device) == cudaSuccess) {
         cudaDeviceSynchronize();
         local_release(s);
-        for (auto &x : s->vars)
-            if (x.second.base) cudaFree(x.second.base);
+        for (auto &x : s->vars) free_shard(x.second);
         for (void *z : s->zombies) cudaFree(z);
+        for (auto &b : s->zombie_blocks) dds_vmm::release(&b);
         if (s->scr.status) cudaFree(s->scr.status);
         if (s->scr.counters) cudaFree(s->scr.counters);
         if (s->scr.req_src) cudaFree(s->scr.req_src);
