@@ -313,6 +313,18 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     const int64_t gwarp = (int64_t)blockIdx.x * NW + warp;
     const int64_t nwarps = (int64_t)gridDim.x * NW;
 
+    // Programmatic dependent launch: let the NEXT kernel of the stream start launching right away (its CTAs
+    // take over each SM as ours retire), and do not touch global memory before the PREVIOUS kernel (which may
+    // have produced our indices / plan, and resets the ticket counters) has completed and flushed.
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[warp][s]), 1);
+        fence_mbar_init();
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncwarp();
+
     // ---- total bytes, segment geometry -------------------------------------------------------
     ChunkWalker<FIXED, CH> w;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
@@ -345,12 +357,6 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
 
     // ---- per-warp pipeline -------------------------------------------------------------------
     const uint32_t ring = smem_u32(smem_dyn) + (uint32_t)warp * (uint32_t)(S * STAGE);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[warp][s]), 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
 
     uint32_t issued = 0, consumed = 0;
     bool more = w.nseg > 0;
@@ -541,6 +547,7 @@ constexpr Geometry kGeoms[] = {{8, 4, 4096}, {8, 6, 4096}, {16, 3, 4096}, {4, 4,
 int g_geom = -1;
 int g_sms = 0;
 int g_ctas_per_sm = 1;
+int g_pdl = 1;
 
 int pick_geometry() {
     if (g_geom >= 0) return 0;
@@ -551,6 +558,7 @@ int pick_geometry() {
     if (const char *e = getenv("DDS_GATHER_GEOM")) g = atoi(e); // tuning knob (kernel variants, not backends)
     if (g < 0 || g >= (int)(sizeof(kGeoms) / sizeof(kGeoms[0]))) g = 0;
     if (const char *e = getenv("DDS_GATHER_CTAS_PER_SM")) g_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
     g_geom = g;
     return 0;
 }
@@ -568,9 +576,18 @@ int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
     }
     int per_sm = g_ctas_per_sm;
     while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;
-    kern<<<g_sms * per_sm, NW * 32, smem, stream>>>(args);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g_sms * per_sm));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("DDS_COMM_TIMEOUT_S", "40")  # a wedged rank should fail a test in seconds, not minutes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
