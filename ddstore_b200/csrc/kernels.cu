@@ -160,10 +160,13 @@ struct GatherArgs {
     unsigned int *counters;
 };
 
-struct Chunk {
-    uint64_t src;
-    int64_t dpos; // byte position in the packed buffer
-    uint32_t n;
+// One pipeline stage carries a GROUP of up to 32 pieces (one per lane): consecutive requests of the walk, or one
+// <= CH-byte piece of a large request. Small requests therefore still put ~CH bytes in flight per stage.
+struct Piece {
+    uint64_t src;  // first payload byte (0: nothing to copy)
+    int64_t dpos;  // byte position in the packed buffer
+    uint32_t n;    // payload bytes (0: lane idle)
+    uint32_t off;  // byte offset of this piece's aligned superset inside the stage
 };
 
 template <bool FIXED, int CH>
@@ -210,13 +213,15 @@ struct ChunkWalker {
         return lo;
     }
 
-    __device__ __forceinline__ bool next(const GatherArgs &a, int lane, Chunk &c) {
+    // Next group of the walk. Returns the bytes to expect in the stage (0: no more work); `pc` is this lane's piece.
+    template <int STAGE>
+    __device__ __forceinline__ uint32_t next_group(const GatherArgs &a, int lane, Piece &pc) {
         while (true) {
             if (seg_pos >= seg_end) {
                 unsigned int seg = 0;
                 if (lane == 0) seg = atomicAdd(&a.counters[0], 1u);
                 seg = __shfl_sync(0xffffffffu, seg, 0);
-                if ((int64_t)seg >= nseg) return false;
+                if ((int64_t)seg >= nseg) return 0;
                 seg_pos = (int64_t)seg * seg_bytes;
                 seg_end = min(T, seg_pos + seg_bytes);
                 r = FIXED ? seg_pos / nb : locate_var(a, seg_pos, lane);
@@ -226,24 +231,62 @@ struct ChunkWalker {
                 continue;
             }
             if (r < win_base || r >= win_base + 32) load_window(a, lane);
-            int wl = (int)(r - win_base);
-            uint64_t src = __shfl_sync(0xffffffffu, w_src, wl);
-            int64_t d0 = __shfl_sync(0xffffffffu, w_dst, wl);
-            int64_t n = __shfl_sync(0xffffffffu, w_n, wl);
-            int64_t req_end = d0 + n;
-            if (req_end <= seg_pos) {
-                r++;
-                continue;
+            {   // fast path: the current request alone (nearly) fills a stage, or is cut by CH / the segment end
+                const int wl = (int)(r - win_base);
+                const uint64_t s0 = __shfl_sync(0xffffffffu, w_src, wl);
+                const int64_t d0 = __shfl_sync(0xffffffffu, w_dst, wl);
+                const int64_t e0 = d0 + __shfl_sync(0xffffffffu, w_n, wl);
+                const int64_t p0 = max(d0, seg_pos);
+                const int64_t len = min(min(e0, seg_end) - p0, (int64_t)CH);
+                if (len >= CH / 2 || p0 + len < e0) {
+                    seg_pos = p0 + len;
+                    if (seg_pos >= e0) r++;
+                    if (s0 == 0) continue; // rejected request (FIXED): its slot stays untouched
+                    const uint64_t src = s0 + (uint64_t)(p0 - d0);
+                    pc.src = lane == 0 ? src : 0;
+                    pc.dpos = p0;
+                    pc.n = lane == 0 ? (uint32_t)len : 0u;
+                    pc.off = 0;
+                    return ((uint32_t)(src & 15u) + (uint32_t)len + 15u) & ~15u;
+                }
             }
-            int64_t stop = min(req_end, seg_end);
-            int64_t len = min((int64_t)CH, stop - seg_pos);
-            c.src = src ? src + (uint64_t)(seg_pos - d0) : 0;
-            c.dpos = seg_pos;
-            c.n = (uint32_t)len;
-            seg_pos += len;
-            if (seg_pos >= req_end) r++;
-            if (src == 0) continue; // rejected request (FIXED): leave its slot untouched
-            return true;
+            // group path: lane j looks at request r + j (as long as the 32-entry window covers it)
+            const int srcl = (int)(r - win_base) + lane;
+            const uint64_t q_src = __shfl_sync(0xffffffffu, w_src, srcl & 31);
+            const int64_t q_d0 = __shfl_sync(0xffffffffu, w_dst, srcl & 31);
+            const int64_t q_n = __shfl_sync(0xffffffffu, w_n, srcl & 31);
+            const int64_t q_end = q_d0 + q_n;
+            const bool valid = srcl < 32 && r + lane < a.nreq && q_d0 < seg_end;
+            const int64_t p0 = max(q_d0, seg_pos);
+            int64_t len = min(q_end, seg_end) - p0;
+            len = max(len, (int64_t)0);
+            len = min(len, (int64_t)CH);
+            const bool complete = p0 + len >= q_end; // this piece finishes its request
+            const bool copy = valid && len > 0 && q_src != 0;
+            const uint64_t src = q_src + (uint64_t)(p0 - q_d0);
+            const uint32_t sz = copy ? (((uint32_t)(src & 15u) + (uint32_t)len + 15u) & ~15u) : 0u;
+            uint32_t end = sz; // inclusive scan of the padded sizes -> stage offsets
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, end, d);
+                if (lane >= d) end += o;
+            }
+            const unsigned ok = __ballot_sync(0xffffffffu, valid && end <= (uint32_t)STAGE);
+            const unsigned part = __ballot_sync(0xffffffffu, valid && !complete);
+            int m = ok == 0xffffffffu ? 32 : __ffs(~ok) - 1;   // leading lanes that are valid and fit
+            if (part) m = min(m, __ffs(part));                  // ... up to and including the first partial piece
+            // lane 0 is always valid and fits (STAGE >= CH + 30), so m >= 1
+            const bool active = lane < m;
+            const int64_t new_pos = __shfl_sync(0xffffffffu, p0 + len, m - 1);
+            const uint32_t total = __shfl_sync(0xffffffffu, end, m - 1);
+            r += __popc(__ballot_sync(0xffffffffu, active && complete));
+            seg_pos = max(seg_pos, new_pos);
+            if (total == 0) continue; // only empty / rejected requests in this run
+            pc.src = (active && copy) ? src : 0;
+            pc.dpos = p0;
+            pc.n = (active && copy) ? (uint32_t)len : 0u;
+            pc.off = end - sz;
+            return total;
         }
     }
 };
@@ -303,10 +346,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     constexpr int STAGE = CH + 32; // room for the aligned superset of a misaligned CH-byte range
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[NW][S];
-    __shared__ __align__(16) struct StageDesc {
+    __shared__ __align__(16) struct PieceDesc {
         int64_t dpos;
-        uint32_t n, a;
-    } desc[NW][S];
+        uint32_t n, pack; // pack = stage offset | (source misalignment << 16)
+    } desc[NW][S][32];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -361,31 +404,33 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     uint32_t issued = 0, consumed = 0;
     bool more = w.nseg > 0;
     while (true) {
-        // issue up to S-1 chunks ahead
+        // issue up to S-1 groups ahead
         while (more && issued - consumed < (uint32_t)(S - 1)) {
-            Chunk c;
-            if (!w.next(a, lane, c)) {
+            Piece pc;
+            const uint32_t total = w.template next_group<STAGE>(a, lane, pc);
+            if (total == 0) {
                 more = false;
                 break;
             }
             const uint32_t st = issued % S;
+            const uint32_t bar = smem_u32(&full_bar[warp][st]);
             if (lane == 0) {
-                // the stage's previous tenant was drained >= 2 consumes ago; its bulk store (if any) is
-                // at most the second most recent group of this thread
+                // the stage's previous tenant was drained >= 2 drains ago; its bulk stores (if any) are at most
+                // the second most recent bulk group of this thread
                 bulk_wait_read<1>();
-                const uint32_t al = (uint32_t)(c.src & 15u);
-                const uint32_t sz = (al + c.n + 15u) & ~15u;
-                desc[warp][st].dpos = c.dpos;
-                desc[warp][st].n = c.n;
-                desc[warp][st].a = al;
-                const uint32_t bar = smem_u32(&full_bar[warp][st]);
-                mbar_expect_tx(bar, sz);
-                tma_load_1d(ring + st * STAGE, (const void *)(c.src - al), sz, bar);
+                mbar_expect_tx(bar, total);
             }
+            __syncwarp();
+            const uint32_t al = (uint32_t)(pc.src & 15u);
+            desc[warp][st][lane].dpos = pc.dpos;
+            desc[warp][st][lane].n = pc.n;
+            desc[warp][st][lane].pack = pc.off | (al << 16);
+            if (pc.n) // every lane issues its own piece's TMA load; all complete on the stage's mbarrier
+                tma_load_1d(ring + st * STAGE + pc.off, (const void *)(pc.src - al), (al + pc.n + 15u) & ~15u, bar);
             issued++;
         }
         if (consumed == issued) break;
-        // drain the oldest chunk
+        // drain the oldest group
         const uint32_t st = consumed % S;
         const uint32_t parity = (consumed / S) & 1u;
         const uint32_t bar = smem_u32(&full_bar[warp][st]);
@@ -399,11 +444,19 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             }
         }
         __syncwarp();
-        const int64_t dpos = desc[warp][st].dpos;
-        const uint32_t n = desc[warp][st].n;
-        const uint32_t al = desc[warp][st].a;
-        drain_chunk<CH>(ring + st * STAGE, al, a.dst + dpos, n, lane);
-        if (lane == 0) bulk_commit(); // one (possibly empty) group per drained chunk
+        const int64_t my_dpos = desc[warp][st][lane].dpos;
+        const uint32_t my_n = desc[warp][st][lane].n;
+        const uint32_t my_pack = desc[warp][st][lane].pack;
+        unsigned todo = __ballot_sync(0xffffffffu, my_n != 0);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t dpos = __shfl_sync(0xffffffffu, my_dpos, j);
+            const uint32_t n = __shfl_sync(0xffffffffu, my_n, j);
+            const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, j);
+            drain_chunk<CH>(ring + st * STAGE + (pk & 0xffffu), pk >> 16, a.dst + dpos, n, lane);
+        }
+        if (lane == 0) bulk_commit(); // one (possibly empty) bulk group per drained stage
         __syncwarp();                 // all lanes are done reading the stage before it is refilled
         consumed++;
     }
@@ -543,24 +596,41 @@ struct Geometry {
     int nw, stages, ch;
 };
 constexpr Geometry kGeoms[] = {{8, 4, 4096}, {8, 6, 4096}, {16, 3, 4096}, {4, 4, 8192}, {12, 4, 4096}, {4, 6, 4096}};
+constexpr int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 
-int g_geom = -1;
+// Measured on B200 (profiles/r1_configs.md): 12 warps x 4 stages is as fast as 8 x 4 on 4 KiB+ rows and clearly
+// faster on the instruction-heavier variable / re-phase path; rows under 2 KiB want even more warps (16 x 3).
+constexpr int kGeomLarge = 4, kGeomSmall = 2, kGeomVar = 4;
+
+int g_geom_fixed_env = -1; // DDS_GATHER_GEOM      (tuning: force one variant for the fixed-count entry)
+int g_geom_var_env = -1;   // DDS_GATHER_GEOM_VAR  (... for the variable-count entry; defaults to the former)
+bool g_geom_init = false;
 int g_sms = 0;
 int g_ctas_per_sm = 1;
 int g_pdl = 1;
 
 int pick_geometry() {
-    if (g_geom >= 0) return 0;
+    if (g_geom_init) return 0;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    int g = 0;
-    if (const char *e = getenv("DDS_GATHER_GEOM")) g = atoi(e); // tuning knob (kernel variants, not backends)
-    if (g < 0 || g >= (int)(sizeof(kGeoms) / sizeof(kGeoms[0]))) g = 0;
+    if (const char *e = getenv("DDS_GATHER_GEOM")) g_geom_fixed_env = atoi(e);
+    if (g_geom_fixed_env >= kNumGeoms) g_geom_fixed_env = -1;
+    g_geom_var_env = g_geom_fixed_env;
+    if (const char *e = getenv("DDS_GATHER_GEOM_VAR")) g_geom_var_env = atoi(e);
+    if (g_geom_var_env >= kNumGeoms) g_geom_var_env = -1;
     if (const char *e = getenv("DDS_GATHER_CTAS_PER_SM")) g_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
-    g_geom = g;
+    g_geom_init = true;
     return 0;
+}
+
+int geometry_for(bool fixed, int64_t request_bytes) {
+    if (fixed) {
+        if (g_geom_fixed_env >= 0) return g_geom_fixed_env;
+        return request_bytes < 2048 ? kGeomSmall : kGeomLarge;
+    }
+    return g_geom_var_env >= 0 ? g_geom_var_env : kGeomVar;
 }
 
 template <bool FIXED, int NW, int S, int CH>
@@ -594,7 +664,7 @@ int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
 template <bool FIXED>
 int launch_gather(const GatherArgs &args, cudaStream_t stream) {
     if (int rc = pick_geometry()) return rc;
-    switch (g_geom) {
+    switch (geometry_for(FIXED, FIXED ? args.count * args.var.row_bytes : 0)) {
     case 1: return launch_gather_t<FIXED, 8, 6, 4096>(args, stream);
     case 2: return launch_gather_t<FIXED, 16, 3, 4096>(args, stream);
     case 3: return launch_gather_t<FIXED, 4, 4, 8192>(args, stream);
@@ -619,7 +689,7 @@ void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk
         *ctas = *warps_per_cta = *stages = *chunk_bytes = *smem_bytes = 0;
         return;
     }
-    const Geometry &g = kGeoms[g_geom];
+    const Geometry &g = kGeoms[geometry_for(true, 4096)];
     int smem = g.nw * g.stages * (g.ch + 32);
     int per_sm = g_ctas_per_sm;
     while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;

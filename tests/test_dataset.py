@@ -1,0 +1,105 @@
+"""Loader adapter: DistDataset / RaggedDataset over the batched fetch, against the source
+arrays. The DataLoader path goes through __getitems__ (one launch per variable per batch)."""
+import threading
+import uuid
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(P, body):
+    from ddstore_b200 import ShmComm
+    key = "ds" + uuid.uuid4().hex[:10]
+    errs, res = [], [None] * P
+
+    def run(r):
+        try:
+            comm = ShmComm(key, r, P)
+            res[r] = body(comm, r)
+            comm.close()
+        except BaseException:  # noqa: BLE001
+            import traceback
+            errs.append(traceback.format_exc())
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(P)]
+    [t.start() for t in th]
+    [t.join(300) for t in th]
+    assert not errs, "\n".join(errs)
+    return res
+
+
+def test_distdataset_per_sample_and_batched_loader():
+    import torch
+    from ddstore_b200.dataset import DistDataset, make_loader
+    rng = np.random.default_rng(3)
+    N, P = 1000, 2
+    images = rng.integers(0, 2**32, size=(N, 1, 8, 8), dtype=np.uint32).view(np.float32)
+    labels = rng.integers(0, 10, size=N)
+    data = [(images[i], int(labels[i])) for i in range(N)]
+
+    def body(comm, r):
+        ds = DistDataset(data, "train", comm=comm, device=0)
+        assert len(ds) == N
+        for idx in (0, 499, 500, 999, int(rng.integers(N))):
+            val, lab = ds[idx]  # the reference's per-sample path (distdataset.py:79-92)
+            assert val.shape == (1, 8, 8) and val.cpu().numpy().tobytes() == images[idx].tobytes() and lab == labels[idx]
+        seen = []
+        loader = make_loader(ds, batch_size=64, rank=r, world_size=P, shuffle=True, seed=7)
+        for epoch in range(2):
+            loader.sampler.set_epoch(epoch)
+            order = []
+            for vals, labs in loader:
+                ds_idx = None
+                assert vals.is_cuda and vals.shape[1:] == (1, 8, 8)
+                order.append((vals.cpu().numpy(), labs.cpu().numpy()))
+            got = np.concatenate([o[0] for o in order])
+            gl = np.concatenate([o[1] for o in order])
+            idx = np.array(list(iter(loader.sampler)))  # same epoch -> same permutation
+            assert got.tobytes() == images[idx].tobytes() and np.array_equal(gl, labels[idx])
+            seen.append(idx)
+        assert not np.array_equal(seen[0], seen[1])  # epoch shuffle
+        ds.free()
+        return set(seen[0].tolist())
+
+    parts = _world(P, body)
+    assert parts[0] | parts[1] == set(range(N))
+
+
+def test_ragged_dataset_config4_shape():
+    import torch
+    from ddstore_b200.dataset import RaggedDataset
+    rng = np.random.default_rng(8)
+    P, per = 2, 300
+    world = []
+    for r in range(P):
+        n = rng.integers(8, 200, size=per)
+        e = 8 * n
+        feat = rng.integers(0, 2**32, size=(int(n.sum()), 16), dtype=np.uint32).view(np.float32)
+        edge = rng.integers(-2**40, 2**40, size=(int(e.sum()), 2), dtype=np.int64)
+        world.append((n, e, feat, edge))
+
+    def sample(i):
+        r, j = divmod(i, per)
+        n, e, feat, edge = world[r]
+        ns, es = np.concatenate([[0], np.cumsum(n)]), np.concatenate([[0], np.cumsum(e)])
+        return feat[ns[j]:ns[j + 1]], edge[es[j]:es[j + 1]]
+
+    def body(comm, r):
+        n, e, feat, edge = world[r]
+        ds = RaggedDataset({"node_feat": feat, "edge_index": edge}, {"node_feat": n, "edge_index": e}, comm=comm, device=0)
+        assert len(ds) == P * per
+        ids = rng.integers(0, P * per, size=97).tolist()
+        batch = ds.__getitems__(ids)
+        f, fo = batch["node_feat"]
+        ed, eo = batch["edge_index"]
+        fo, eo = fo.cpu().numpy(), eo.cpu().numpy()
+        for k, i in enumerate(ids):
+            sf, se = sample(i)
+            assert f[fo[k]:fo[k + 1]].cpu().numpy().tobytes() == sf.tobytes()
+            assert ed[eo[k]:eo[k + 1]].cpu().numpy().tobytes() == se.tobytes()
+        ds.free()
+        return True
+
+    assert all(_world(P, body))
