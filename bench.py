@@ -80,6 +80,18 @@ def np_synth_rows(seed, first_global_row, nrows, disp, dtype):
     return np.ascontiguousarray(raw).view(dtype).reshape(nrows, disp)
 
 
+def bind_to_gpu_numa(gpu_index):
+    """pin this rank to the CPUs next to its GPU (NVML's ideal affinity) so pinned host buffers and the PCIe
+    copies of the e2e path stay on the GPU's NUMA node"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+    except Exception:  # noqa: BLE001 -- best effort
+        pass
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -233,6 +245,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {N} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {N}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa(local)
     if N > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=dev)
         comm = TorchDistComm()

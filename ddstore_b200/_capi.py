@@ -53,6 +53,9 @@ SIGNATURES = {
     "dds_get_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_uint, C.c_void_p, I64P, I64P]),
     "dds_batch_wait": (C.c_int, [C.c_void_p, I64P, I64P]),
+    "dds_set_sample_index": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "dds_get_samples": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_uint, C.c_void_p, I64P, I64P]),
     "dds_query": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(VarInfo)]),
     "dds_epoch_begin": (C.c_int, [C.c_void_p]),
     "dds_epoch_end": (C.c_int, [C.c_void_p]),

@@ -481,6 +481,68 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
 constexpr int PLAN_THREADS = 256;
 constexpr int PLAN_ITEMS = 4;
 constexpr int PLAN_TILE = PLAN_THREADS * PLAN_ITEMS;
+constexpr int PLAN1_THREADS = 1024; // single-CTA plan for small batches
+constexpr int PLAN1_ITEMS = 8;
+constexpr int PLAN1_MAX = PLAN1_THREADS * PLAN1_ITEMS;
+
+// where request i's (start row, row count) comes from: explicit arrays, or a per-sample table indexed by ids[i]
+struct PlanSrc {
+    const int64_t *starts, *counts;       // explicit (ids == nullptr)
+    const int64_t *ids;                   // sample ids (device-resident sample index)
+    const int64_t *tab_start, *tab_count; // [nsamples] row_start / row_count of every sample of this variable
+    int64_t nsamples;
+};
+
+// Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as three unrolled passes
+// (ids, then table rows, then arithmetic) so that the K independent -- and for the sample index, dependent
+// two-level -- global loads of a thread are all in flight together instead of one DRAM latency after another.
+template <int K>
+__device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &p, const int64_t (&idx)[K], int64_t nreq,
+                                          unsigned long long *status, uint64_t (&src)[K], int64_t (&nbytes)[K]) {
+    int64_t start[K], count[K];
+    bool live[K], badid[K];
+    if (p.ids) {
+        int64_t id[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            live[k] = idx[k] < nreq;
+            id[k] = live[k] ? p.ids[idx[k]] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            badid[k] = live[k] && (id[k] < 0 || id[k] >= p.nsamples);
+            const bool ok = live[k] && !badid[k];
+            start[k] = ok ? p.tab_start[id[k]] : 0;
+            count[k] = ok ? p.tab_count[id[k]] : 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            live[k] = idx[k] < nreq;
+            badid[k] = false;
+            start[k] = live[k] ? p.starts[idx[k]] : 0;
+            count[k] = live[k] ? p.counts[idx[k]] : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        src[k] = 0;
+        nbytes[k] = 0;
+        if (!live[k]) continue;
+        if (badid[k]) {
+            report(status, idx[k], DDSK_CODE_SAMPLE);
+            continue;
+        }
+        uint64_t s = 0;
+        const int code = dev_locate(var, start[k], count[k], &s);
+        if (code) {
+            report(status, idx[k], code);
+            continue;
+        }
+        src[k] = s;
+        nbytes[k] = count[k] * var.row_bytes;
+    }
+}
 
 __device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
 #pragma unroll
@@ -491,16 +553,17 @@ __device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
     return v;
 }
 
-// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+// block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, *total = block sum
+template <int NT>
 __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
-    __shared__ int64_t warp_tot[PLAN_THREADS / 32];
+    __shared__ int64_t warp_tot[NT / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int64_t inc = warp_incl_scan(v, lane);
     if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
     int64_t base = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < PLAN_THREADS / 32; k++) {
+    for (int k = 0; k < NT / 32; k++) {
         int64_t t = warp_tot[k];
         if (k < wid) base += t;
         tot += t;
@@ -510,37 +573,73 @@ __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
     return base + inc - v;
 }
 
-// pass 1: per request source address + byte size (size parked in req_dst), per tile byte sum
+// small batches (<= 8192 requests): the whole plan in ONE CTA, one launch
+__global__ void __launch_bounds__(PLAN1_THREADS) dds_plan_single_kernel(const __grid_constant__ ddsk_var_t var,
+                                                                        const __grid_constant__ PlanSrc p, int64_t nreq,
+                                                                        uint64_t *__restrict__ req_src,
+                                                                        int64_t *__restrict__ req_dst,
+                                                                        int64_t *__restrict__ offsets_out,
+                                                                        unsigned long long *status) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // blocked: thread t owns the ipt (<= 8) consecutive requests [t*ipt, (t+1)*ipt), so every thread has work
+    const int ipt = (int)((nreq + PLAN1_THREADS - 1) / PLAN1_THREADS);
+    const int64_t base = (int64_t)threadIdx.x * ipt;
+    int64_t idx[PLAN1_ITEMS], nb[PLAN1_ITEMS];
+    uint64_t sv[PLAN1_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PLAN1_ITEMS; k++) idx[k] = k < ipt ? base + k : nreq;
+    plan_many<PLAN1_ITEMS>(var, p, idx, nreq, status, sv, nb);
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN1_ITEMS; k++) {
+        if (idx[k] < nreq) {
+            req_src[idx[k]] = sv[k];
+            mine += nb[k];
+        }
+    }
+    int64_t tot;
+    int64_t run = block_excl_scan<PLAN1_THREADS>(mine, &tot);
+#pragma unroll
+    for (int k = 0; k < PLAN1_ITEMS; k++) {
+        if (idx[k] < nreq) {
+            req_dst[idx[k]] = run;
+            if (offsets_out) offsets_out[idx[k]] = run;
+            run += nb[k];
+        }
+    }
+    if (threadIdx.x == 0) {
+        req_dst[nreq] = tot;
+        if (offsets_out) offsets_out[nreq] = tot;
+    }
+}
+
+// pass 1 (large batches): per request source address + byte size (size parked in req_dst), per tile byte sum
 __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __grid_constant__ ddsk_var_t var,
-                                                                       const int64_t *__restrict__ starts,
-                                                                       const int64_t *__restrict__ counts, int64_t nreq,
+                                                                       const __grid_constant__ PlanSrc p, int64_t nreq,
                                                                        uint64_t *__restrict__ req_src,
                                                                        int64_t *__restrict__ req_dst,
                                                                        int64_t *__restrict__ tile_sums,
                                                                        unsigned long long *status) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
+    int64_t idx[PLAN_ITEMS], nb[PLAN_ITEMS];
+    uint64_t sv[PLAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PLAN_ITEMS; k++) idx[k] = base + (int64_t)k * PLAN_THREADS + threadIdx.x; // striped
+    plan_many<PLAN_ITEMS>(var, p, idx, nreq, status, sv, nb);
     int64_t mine = 0;
 #pragma unroll
     for (int k = 0; k < PLAN_ITEMS; k++) {
-        int64_t i = base + (int64_t)k * PLAN_THREADS + threadIdx.x;
-        if (i < nreq) {
-            uint64_t s = 0;
-            int64_t c = counts[i];
-            int code = dev_locate(var, starts[i], c, &s);
-            int64_t nbytes = 0;
-            if (code) {
-                report(status, i, code);
-                s = 0;
-            } else {
-                nbytes = c * var.row_bytes;
-            }
-            req_src[i] = s;
-            req_dst[i] = nbytes;
-            mine += nbytes;
+        if (idx[k] < nreq) {
+            req_src[idx[k]] = sv[k];
+            req_dst[idx[k]] = nb[k];
+            mine += nb[k];
         }
     }
     int64_t tot;
-    block_excl_scan(mine, &tot);
+    block_excl_scan<PLAN_THREADS>(mine, &tot);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
@@ -548,10 +647,12 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __g
 __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nreq, int64_t *__restrict__ req_dst,
                                                                      const int64_t *__restrict__ tile_sums,
                                                                      int64_t *__restrict__ offsets_out) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int64_t part = 0;
     for (int64_t t = threadIdx.x; t < (int64_t)blockIdx.x; t += PLAN_THREADS) part += tile_sums[t];
     int64_t tile_base;
-    block_excl_scan(part, &tile_base);
+    block_excl_scan<PLAN_THREADS>(part, &tile_base);
     // layout inside a tile is striped (item k of thread t = k*THREADS + t): scan stripe by stripe
     const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
     int64_t running = tile_base;
@@ -560,7 +661,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nre
         int64_t i = base + (int64_t)k * PLAN_THREADS + threadIdx.x;
         int64_t v = i < nreq ? req_dst[i] : 0;
         int64_t tot;
-        int64_t ex = block_excl_scan(v, &tot);
+        int64_t ex = block_excl_scan<PLAN_THREADS>(v, &tot);
         if (i < nreq) {
             req_dst[i] = running + ex;
             if (offsets_out) offsets_out[i] = running + ex;
@@ -661,6 +762,24 @@ int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
     return 0;
 }
 
+// launch with the programmatic-dependent-launch attribute (the kernels call griddepcontrol.wait themselves)
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
+    g_launches++;
+    return 0;
+}
+
 template <bool FIXED>
 int launch_gather(const GatherArgs &args, cudaStream_t stream) {
     if (int rc = pick_geometry()) return rc;
@@ -720,9 +839,8 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
     return launch_gather<true>(a, st);
 }
 
-int ddsk_gather_var(const ddsk_var_t *var, const int64_t *starts_dev, const int64_t *counts_dev, int64_t nreq,
-                    void *dst_dev, int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr,
-                    int reset_status, void *stream) {
+int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev, int64_t dst_capacity,
+                    int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0) return 0;
@@ -731,14 +849,27 @@ int ddsk_gather_var(const ddsk_var_t *var, const int64_t *starts_dev, const int6
                  (long long)scr->cap_req);
         return -2;
     }
-    const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
-    dds_plan_lookup_kernel<<<tiles, PLAN_THREADS, 0, st>>>(*var, starts_dev, counts_dev, nreq, scr->req_src, scr->req_dst,
-                                                           scr->tile_sums, scr->status);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    dds_plan_scan_kernel<<<tiles, PLAN_THREADS, 0, st>>>(nreq, scr->req_dst, scr->tile_sums, offsets_dev_or_null);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = pick_geometry()) return rc;
+    PlanSrc p;
+    p.starts = index->starts;
+    p.counts = index->counts;
+    p.ids = index->sample_ids;
+    p.tab_start = index->table_start;
+    p.tab_count = index->table_count;
+    p.nsamples = index->nsamples;
+    if (nreq <= PLAN1_MAX) {
+        if (int rc = launch_pdl(dds_plan_single_kernel, dim3(1), dim3(PLAN1_THREADS), st, *var, p, nreq, scr->req_src,
+                                scr->req_dst, offsets_dev_or_null, scr->status))
+            return rc;
+    } else {
+        const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
+        if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq, scr->req_src,
+                                scr->req_dst, scr->tile_sums, scr->status))
+            return rc;
+        if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
+                                (const int64_t *)scr->tile_sums, offsets_dev_or_null))
+            return rc;
+    }
     GatherArgs a;
     memset(&a, 0, sizeof(a));
     a.var = *var;

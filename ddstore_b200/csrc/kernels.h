@@ -29,6 +29,7 @@ typedef struct ddsk_var {
 #define DDSK_CODE_COUNT 3
 #define DDSK_CODE_CAPACITY 12
 #define DDSK_CODE_WATCHDOG 14
+#define DDSK_CODE_SAMPLE 15
 
 /* scratch a store owns for the batched path (all device memory) */
 typedef struct ddsk_scratch {
@@ -46,10 +47,19 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
                       int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
                       void *stream);
 
+/* Where the (start row, row count) of request i comes from (all device pointers): explicit arrays, or -- when
+ * sample_ids is set -- the per-sample table of the variable: start = table_start[sample_ids[i]], etc. */
+typedef struct ddsk_index {
+    const int64_t *starts, *counts;
+    const int64_t *sample_ids;
+    const int64_t *table_start, *table_count;
+    int64_t nsamples;
+} ddsk_index_t;
+
 /* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. */
-int ddsk_gather_var(const ddsk_var_t *var, const int64_t *starts_dev, const int64_t *counts_dev, int64_t nreq,
-                    void *dst_dev, int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr,
-                    int reset_status, void *stream);
+int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev,
+                    int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                    void *stream);
 
 /* Synthetic payload: element (global_row g, col c) = low itemsize bytes of
  * splitmix64(seed ^ (g*disp + c)). Bench / test helper, fills a local shard in place. */

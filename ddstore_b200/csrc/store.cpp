@@ -114,6 +114,10 @@ struct Var {
     std::vector<dds_vmm::Block> peer_block;
     bool fence_active = false;
     ddsk_var_t kv;
+    // per-sample index: sample i owns rows [tab_start[i], tab_start[i] + tab_count[i])
+    int64_t *d_tab_start = nullptr, *d_tab_count = nullptr;
+    int64_t nsamples = 0;
+    std::vector<int64_t> h_tab_count;
 };
 
 } // namespace
@@ -213,6 +217,9 @@ void release_var(Var &v, int rank) {
 }
 
 void free_shard(Var &v) {
+    if (v.d_tab_start) cudaFree(v.d_tab_start);
+    if (v.d_tab_count) cudaFree(v.d_tab_count);
+    v.d_tab_start = v.d_tab_count = nullptr;
     if (v.vmm)
         dds_vmm::release(&v.block);
     else if (v.base)
@@ -409,6 +416,7 @@ int decode_status_word(unsigned long long st, int64_t *bad_index) {
     case DDSK_CODE_CAPACITY:
         if (bad_index) *bad_index = -1;
         return fail(DDS_ERR_CAPACITY);
+    case DDSK_CODE_SAMPLE: return fail(DDS_ERR_ARG, "sample id outside the variable's sample index");
     default: return fail(DDS_ERR_WATCHDOG);
     }
 }
@@ -560,19 +568,16 @@ int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nro
     return DDS_OK;
 }
 
-int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const int64_t *counts,
-                  int64_t fixed_count, int64_t nreq, int itemsize, void *dst, int64_t dst_capacity,
-                  int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
-                  int64_t *bad_index) {
-    clear_error();
-    if (bad_index) *bad_index = -1;
-    if (total_bytes) *total_bytes = 0;
-    if (!s) return fail(DDS_ERR_ARG, "null store");
-    Var *v = find_var(s, name);
-    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
-    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE); // ddstore.hpp:202-203
+int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);
+
+// The one batched path behind dds_get_batch / dds_get_samples / dds_get.
+//   by_sample == false: request i = (starts[i], counts ? counts[i] : fixed_count)
+//   by_sample == true : request i = the rows of sample starts[i] (= sample id) in v's per-sample index
+static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *starts, const int64_t *counts,
+                      int64_t fixed_count, int64_t nreq, void *dst, int64_t dst_capacity, int64_t *dst_offsets,
+                      unsigned flags, void *cuda_stream, int64_t *total_bytes, int64_t *bad_index) {
     if (nreq < 0 || dst_capacity < 0) return fail(DDS_ERR_ARG, "negative nreq or capacity");
-    if (nreq > 0 && !starts) return fail(DDS_ERR_ARG, "null starts");
+    if (nreq > 0 && !starts) return fail(DDS_ERR_ARG, "null starts / sample ids");
     const bool idx_dev = flags & DDS_IDX_ON_DEVICE, dst_dev = flags & DDS_DST_ON_DEVICE;
     const bool no_sync = flags & DDS_NO_SYNC;
     if (no_sync && !(idx_dev && dst_dev)) return fail(DDS_ERR_ARG, "async batches need device indices and a device destination");
@@ -585,7 +590,7 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
         if (int rc = dds_batch_wait(s, nullptr, nullptr)) return rc;
     }
     const int64_t R = v->kv.row_bytes;
-    const bool fixed = counts == nullptr;
+    const bool fixed = !by_sample && counts == nullptr;
 
     if (nreq == 0) {
         if (dst_offsets) {
@@ -597,13 +602,13 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
         return DDS_OK;
     }
 
-    // ---- indices to the device (16 B per request)
+    // ---- indices to the device (8-16 B per request)
     const int64_t *d_starts = starts, *d_counts = counts;
     if (!idx_dev) {
         if (int rc = ensure_idx(s, nreq)) return rc;
         CU(cudaMemcpyAsync(s->d_starts, starts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
         d_starts = s->d_starts;
-        if (!fixed) {
+        if (!fixed && !by_sample) {
             CU(cudaMemcpyAsync(s->d_counts, counts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
             d_counts = s->d_counts;
         }
@@ -616,9 +621,15 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
     int64_t upper = -1; // upper bound of the packed bytes (== total when every request is valid)
     if (fixed)
         upper = fixed_count > 0 ? nreq * fixed_count * R : 0;
-    else if (!idx_dev) {
+    else if (!idx_dev && !by_sample) {
         upper = 0;
         for (int64_t i = 0; i < nreq; i++) upper += counts[i] > 0 ? counts[i] * R : 0;
+    } else if (!idx_dev && by_sample && !v->h_tab_count.empty()) {
+        upper = 0;
+        for (int64_t i = 0; i < nreq; i++) {
+            const int64_t id = starts[i];
+            if (id >= 0 && id < v->nsamples) upper += v->h_tab_count[(size_t)id] > 0 ? v->h_tab_count[(size_t)id] * R : 0;
+        }
     }
 
     // ---- destination: the caller's device buffer, or the store's staging buffer for a host destination
@@ -635,10 +646,22 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
     // ---- launch
     int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
     int krc;
-    if (fixed)
+    if (fixed) {
         krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
-    else
-        krc = ddsk_gather_var(&v->kv, d_starts, d_counts, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
+    } else {
+        ddsk_index_t ix;
+        memset(&ix, 0, sizeof(ix));
+        if (by_sample) {
+            ix.sample_ids = d_starts;
+            ix.table_start = v->d_tab_start;
+            ix.table_count = v->d_tab_count;
+            ix.nsamples = v->nsamples;
+        } else {
+            ix.starts = d_starts;
+            ix.counts = d_counts;
+        }
+        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
+    }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
     s->pending_fixed_total = fixed ? upper : -1;
@@ -671,6 +694,61 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
     CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = fixed ? upper : (int64_t)s->h_status[1];
     return decode_status(s, st, s->h_status[0], bad_index);
+}
+
+int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const int64_t *counts,
+                  int64_t fixed_count, int64_t nreq, int itemsize, void *dst, int64_t dst_capacity,
+                  int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
+                  int64_t *bad_index) {
+    clear_error();
+    if (bad_index) *bad_index = -1;
+    if (total_bytes) *total_bytes = 0;
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE); // ddstore.hpp:202-203
+    return batch_impl(s, v, false, starts, counts, fixed_count, nreq, dst, dst_capacity, dst_offsets, flags, cuda_stream,
+                      total_bytes, bad_index);
+}
+
+int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_start, const int64_t *row_count,
+                         int64_t nsamples, int tables_on_device) {
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (nsamples < 0 || (nsamples > 0 && (!row_start || !row_count))) return fail(DDS_ERR_ARG, "bad sample index");
+    CU(cudaSetDevice(s->device));
+    if (v->d_tab_start) cudaFree(v->d_tab_start);
+    if (v->d_tab_count) cudaFree(v->d_tab_count);
+    v->d_tab_start = v->d_tab_count = nullptr;
+    v->h_tab_count.clear();
+    v->nsamples = 0;
+    if (nsamples == 0) return DDS_OK;
+    CU(cudaMalloc((void **)&v->d_tab_start, (size_t)nsamples * 8));
+    CU(cudaMalloc((void **)&v->d_tab_count, (size_t)nsamples * 8));
+    const cudaMemcpyKind kind = tables_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(v->d_tab_start, row_start, (size_t)nsamples * 8, kind, s->stream));
+    CU(cudaMemcpyAsync(v->d_tab_count, row_count, (size_t)nsamples * 8, kind, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (!tables_on_device) v->h_tab_count.assign(row_count, row_count + nsamples); // sizes a host destination needs
+    v->nsamples = nsamples;
+    return DDS_OK;
+}
+
+int dds_get_samples(dds_store_t *s, const char *name, const int64_t *sample_ids, int64_t nreq, int itemsize, void *dst,
+                    int64_t dst_capacity, int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
+                    int64_t *bad_index) {
+    clear_error();
+    if (bad_index) *bad_index = -1;
+    if (total_bytes) *total_bytes = 0;
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE);
+    if (!v->d_tab_start) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
+    return batch_impl(s, v, true, sample_ids, nullptr, 0, nreq, dst, dst_capacity, dst_offsets, flags, cuda_stream,
+                      total_bytes, bad_index);
 }
 
 // completes a batch issued with DDS_NO_SYNC

@@ -145,12 +145,14 @@ class RaggedDataset(Dataset):
             buf[0, :len(cnt)], buf[1, :len(cnt)] = local_start, cnt
             parts = self.comm.allgather_bytes(buf.tobytes())
             tabs = [np.frombuffer(p, np.int64).reshape(2, pad)[:, :n] for p, n in zip(parts, sizes)]
-            self.starts[name] = torch.from_numpy(np.concatenate([t[0] for t in tabs])).to(self.device)
-            self.counts[name] = torch.from_numpy(np.concatenate([t[1] for t in tabs])).to(self.device)
+            all_start = np.concatenate([t[0] for t in tabs])
+            all_count = np.concatenate([t[1] for t in tabs])
+            self.ddstore.set_sample_index(name, all_start, all_count)  # device-resident (start, count) of every sample
+            self.counts[name] = all_count
             self.row_bytes[name] = arr.dtype.itemsize * int(np.prod(arr.shape[1:], dtype=np.int64))
             self.dtypes[name] = torch.from_numpy(arr[:0]).dtype
             self.widths[name] = arr.shape[1:]
-        self.total_ns = int(self.starts[self.names[0]].numel())
+        self.total_ns = int(len(self.counts[self.names[0]]))
 
     def __len__(self):
         return self.total_ns
@@ -159,18 +161,17 @@ class RaggedDataset(Dataset):
         return self.__getitems__([idx])
 
     def __getitems__(self, indices):
-        """-> {name: (packed rows tensor [sum(count), ...width], int64 row offsets per sample [B+1])}"""
-        ids = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(self.device, non_blocking=True)
+        """-> {name: (packed rows tensor [sum(count), ...width], int64 row offsets per sample [B+1])}.
+        One launch chain per variable; the sample-id -> (start, count) lookup happens on the device."""
+        ids = np.asarray(indices, dtype=np.int64)
+        d_ids = torch.from_numpy(ids).to(self.device, non_blocking=True)
         out = {}
         for name in self.names:
-            st, ct = self.starts[name][ids], self.counts[name][ids]
-            rows = int(ct.sum().item())
-            buf = torch.empty((rows,) + tuple(self.widths[name]), dtype=self.dtypes[name], device=self.device)
-            offs = torch.empty(len(indices) + 1, dtype=torch.int64, device=self.device)
-            if rows or len(indices):
-                self.ddstore.get_batch(name, st, ct, out=buf if rows else torch.empty(16, dtype=torch.uint8, device=self.device),
-                                       offsets=offs)
-            out[name] = (buf, offs // self.row_bytes[name])
+            rows = int(self.counts[name][ids].sum())  # host-side size of the packed result (sizes only, no data)
+            buf = torch.empty((max(rows, 1),) + tuple(self.widths[name]), dtype=self.dtypes[name], device=self.device)
+            offs = torch.empty(len(ids) + 1, dtype=torch.int64, device=self.device)
+            self.ddstore.get_samples(name, d_ids, out=buf, offsets=offs)
+            out[name] = (buf[:rows], offs // self.row_bytes[name])
         return out
 
     collate = staticmethod(lambda batch: batch)

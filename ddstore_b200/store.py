@@ -153,6 +153,49 @@ class PyDDStore:
         _capi.raise_for(rc)
         return total.value
 
+    # ---------------------------------------------------------------- per-sample index (variable-length datasets)
+    def set_sample_index(self, name, row_start, row_count):
+        """Register, for variable `name`, which GLOBAL rows every sample owns: sample i = rows
+        [row_start[i], row_start[i] + row_count[i]). Tables: int64 host arrays or CUDA tensors; copied once."""
+        dev = hasattr(row_start, "data_ptr") and getattr(row_start, "is_cuda", False)
+        if dev:
+            n, sp, cp, keep = row_start.numel(), row_start.data_ptr(), row_count.data_ptr(), (row_start, row_count)
+        else:
+            sa, ca = _i64(row_start), _i64(row_count)
+            n, sp, cp, keep = sa.size, sa.ctypes.data, ca.ctypes.data, (sa, ca)
+        _capi.raise_for(self._L.dds_set_sample_index(self._h, name.encode(), sp, cp, n, 1 if dev else 0))
+        del keep
+
+    def get_samples(self, name, sample_ids, out, offsets=None, stream=None, wait=True):
+        """get_batch by SAMPLE ID: the id -> (start, count) lookup runs inside the launch, against the index
+        registered with set_sample_index. Same packing / offsets / error behaviour as get_batch."""
+        itemsize = self._itemsize.get(name)
+        if itemsize is None:
+            itemsize = self._itemsize[name] = self.query(name)["itemsize"]
+        ob = _Buf(out, writable=True)
+        s_dev = hasattr(sample_ids, "data_ptr") and getattr(sample_ids, "is_cuda", False)
+        if s_dev:
+            nreq, sp, keep = sample_ids.numel(), sample_ids.data_ptr(), sample_ids
+        else:
+            sa = _i64(sample_ids)
+            nreq, sp, keep = sa.size, sa.ctypes.data, sa
+        flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | (_capi.DST_ON_DEVICE if ob.on_device else 0)
+        if not wait:
+            flags |= _capi.NO_SYNC
+        op = None
+        if offsets is not None:
+            fb = _Buf(offsets, writable=True)
+            if fb.on_device != ob.on_device or fb.itemsize != 8 or fb.size < nreq + 1:
+                raise ValueError("offsets must be int64[len(sample_ids)+1] with the same residency as out")
+            op = fb.ptr
+        total, bad = C.c_int64(0), C.c_int64(-1)
+        rc = self._L.dds_get_samples(self._h, name.encode(), sp, nreq, itemsize, ob.ptr, ob.nbytes, op, flags,
+                                     self._stream_arg(stream), C.byref(total), C.byref(bad))
+        del keep
+        self.last_bad_index = bad.value
+        _capi.raise_for(rc)
+        return total.value
+
     @staticmethod
     def _stream_arg(stream):
         """None -> the store's own stream; a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)

@@ -132,6 +132,17 @@ int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const
                   int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
                   int64_t *bad_index);
 
+/* Per-sample index of a variable (variable-length / multi-array datasets): sample i owns global rows
+ * [row_start[i], row_start[i] + row_count[i]) -- the (start, count) pairs a HydraGNN-style loader passes to
+ * get(name, arr, start) with count = arr.shape[0] (src/pyddstore.pyx:84-87). The tables are copied to the device
+ * once; dds_get_samples then needs only the sample ids: the id -> (start, count) lookup is fused into the launch. */
+int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_start, const int64_t *row_count,
+                         int64_t nsamples, int tables_on_device);
+/* dds_get_batch with request i = the rows of sample sample_ids[i]. Same flags, packing, offsets and error rules. */
+int dds_get_samples(dds_store_t *s, const char *name, const int64_t *sample_ids, int64_t nreq, int itemsize, void *dst,
+                    int64_t dst_capacity, int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
+                    int64_t *bad_index);
+
 /* Completes the batch issued with DDS_NO_SYNC (stream sync + status decode). */
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);
 

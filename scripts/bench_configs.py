@@ -111,6 +111,10 @@ def main():
             offs = torch.empty(B + 1, dtype=torch.int64, device=dev)
             timed(lambda: store.get_batch("x", st, ct, out=out, offsets=offs, stream=side.cuda_stream, wait=False), nbytes,
                   f"cfg3 variable 100-10000 f32 (4-byte aligned rows), B={B}", {"samples": nsamp})
+            if B == 4096:
+                store.set_sample_index("x", d_start, d_len)
+            timed(lambda: store.get_samples("x", ids, out, offsets=offs, stream=side.cuda_stream, wait=False), nbytes,
+                  f"cfg3 by sample id (device index), B={B}", {"samples": nsamp})
         store.free()
         store = PyDDStore(comm, device=local)
 

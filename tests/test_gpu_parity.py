@@ -376,3 +376,42 @@ def test_full_size_config2_spot_check(coracle):
         return True
 
     assert all(run_world(1, body, timeout=900))
+
+
+def test_sample_index_lookup_fused_in_the_launch(coracle):
+    """get_samples(ids) == get_batch(starts[ids], counts[ids]), small (1-CTA plan) and large
+    (2-kernel plan) batches, host and device ids, plus out-of-range ids."""
+    torch = _torch()
+    rng = np.random.default_rng(21)
+    P, nsamp = 3, 9000
+    L = rng.integers(0, 40, size=nsamp)  # some empty samples
+    sstart = np.concatenate([[0], np.cumsum(L)])
+    per = nsamp // P
+    shards = []
+    for r in range(P):
+        n = int(sstart[(r + 1) * per] - sstart[r * per])
+        shards.append(rng.integers(0, 256, size=(n, 5), dtype=np.uint8))
+
+    def body(store, r):
+        store.add("x", shards[r])
+        store.set_sample_index("x", sstart[:-1], L)
+        for B in (300, 20000):
+            ids = rng.integers(0, nsamp, size=B)
+            exp, exp_offs, bad, _ = coracle.get_batch(shards, sstart[ids], L[ids])
+            assert bad == -1
+            out = np.zeros(max(exp.size, 1), np.uint8)
+            offs = np.zeros(B + 1, np.int64)
+            assert store.get_samples("x", ids, out, offsets=offs) == exp.size
+            assert out[:exp.size].tobytes() == exp.tobytes() and offs.tolist() == exp_offs.tolist()
+            d_out = torch.zeros(max(exp.size, 16), dtype=torch.uint8, device="cuda:0")
+            assert store.get_samples("x", torch.from_numpy(ids).cuda(), d_out) == exp.size
+            assert d_out[:exp.size].cpu().numpy().tobytes() == exp.tobytes()
+        ids = np.array([5, 6, nsamp, 7])
+        with pytest.raises(ValueError, match="sample id"):
+            store.get_samples("x", ids, np.zeros(4096, np.uint8))
+        assert store.last_bad_index == 2
+        with pytest.raises(ValueError, match="sample id"):
+            store.get_samples("x", [-1], np.zeros(16, np.uint8))
+        return True
+
+    assert all(run_world(P, body))
