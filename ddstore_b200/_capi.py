@@ -49,6 +49,8 @@ SIGNATURES = {
     "dds_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "dds_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, C.c_int]),
     "dds_update": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "dds_update_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                   C.c_void_p]),
     "dds_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
     "dds_get_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_uint, C.c_void_p, I64P, I64P]),

@@ -549,8 +549,8 @@ int dds_init(dds_store_t *s, const char *name, int64_t nrows, int disp, int item
     return register_var(s, name, nullptr, nrows, disp, itemsize, 0, true);
 }
 
-int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
-               int buffer_on_device) {
+static int update_impl(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
+                       int buffer_on_device, cudaStream_t st, bool sync) {
     clear_error();
     if (!s) return fail(DDS_ERR_ARG, "null store");
     Var *v = find_var(s, name);
@@ -562,10 +562,21 @@ int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nro
     const size_t row = (size_t)v->disp * (size_t)v->itemsize;
     if (nrows * (int64_t)row > 0) {
         CU(cudaMemcpyAsync((char *)v->base + (size_t)offset * row, buffer, (size_t)nrows * row,
-                           buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+                           buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        if (sync) CU(cudaStreamSynchronize(st));
     }
     return DDS_OK;
+}
+
+int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
+               int buffer_on_device) {
+    return update_impl(s, name, buffer, nrows, offset, itemsize, buffer_on_device, s ? s->stream : nullptr, true);
+}
+
+int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
+                     int buffer_on_device, void *cuda_stream) {
+    return update_impl(s, name, buffer, nrows, offset, itemsize, buffer_on_device,
+                       cuda_stream ? (cudaStream_t)cuda_stream : (s ? s->stream : nullptr), false);
 }
 
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);

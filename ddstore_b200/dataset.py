@@ -187,3 +187,92 @@ def make_loader(dataset, batch_size, rank=0, world_size=1, shuffle=True, seed=0,
                                  drop_last=drop_last)
     return DataLoader(dataset, batch_size=batch_size, sampler=sampler, num_workers=0, collate_fn=dataset.collate,
                       drop_last=drop_last)
+
+
+class PrefetchLoader:
+    """Double-buffered batch prefetch: while the consumer works on batch k, batch k+1 is
+    already being gathered on a side stream into the other buffer set. The reference brackets every batch with
+    epoch_begin/epoch_end around a blocking fetch (examples/vae/vae-ddp.py:240-265); here the fetch of the next
+    batch hides under the training step and the consumer only waits on a CUDA event.
+
+    dataset: a DistDataset; sampler: iterable of sample indices (e.g. DistributedSampler); yields (vals, labels)
+    device tensors that stay valid until the next-but-one iteration (depth = 2 buffer sets).
+    """
+
+    def __init__(self, dataset, sampler, batch_size, drop_last=False, depth=2):
+        self.ds, self.sampler, self.bs, self.drop_last, self.depth = dataset, sampler, batch_size, drop_last, max(2, depth)
+        dev = dataset.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [(torch.empty((batch_size, dataset.sample_size), dtype=dataset.dtype, device=dev),
+                      torch.empty((batch_size, 1), dtype=torch.int32, device=dev),
+                      torch.empty(batch_size, dtype=torch.int64, device=dev)) for _ in range(self.depth)]
+        self.events = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def _batches(self):
+        cur = []
+        for i in self.sampler:
+            cur.append(int(i))
+            if len(cur) == self.bs:
+                yield cur
+                cur = []
+        if cur and not self.drop_last:
+            yield cur
+
+    def _issue(self, slot, idx):
+        vals, labs, d_idx = self.bufs[slot]
+        n = len(idx)
+        host_idx = torch.as_tensor(idx, dtype=torch.int64).pin_memory()
+        with torch.cuda.stream(self.stream):
+            d_idx[:n].copy_(host_idx, non_blocking=True)
+            st = self.stream.cuda_stream
+            self.ds.ddstore.get_batch(f"{self.ds.label}data", d_idx[:n], out=vals[:n], count=1, stream=st, wait=False)
+            self.ds.ddstore.get_batch(f"{self.ds.label}labels", d_idx[:n], out=labs[:n], count=1, stream=st, wait=False)
+            self.events[slot].record(self.stream)
+        return n, host_idx
+
+    def __iter__(self):
+        consumer = torch.cuda.current_stream(self.ds.device)
+        pending = []  # (slot, n, keepalive)
+        slot = 0
+        it = self._batches()
+        for idx in it:
+            # a slot is reused `depth` batches later: make the side stream wait for whatever the consumer queued so far
+            self.stream.wait_stream(consumer)
+            n, keep = self._issue(slot, idx)
+            pending.append((slot, n, keep))
+            slot = (slot + 1) % self.depth
+            if len(pending) == self.depth:
+                yield self._take(pending.pop(0), consumer)
+        while pending:
+            yield self._take(pending.pop(0), consumer)
+        self.ds.ddstore.wait()  # surface any fetch error of the epoch
+
+    def _take(self, item, consumer):
+        slot, n, _ = item
+        consumer.wait_event(self.events[slot])
+        vals, labs, _ = self.bufs[slot]
+        return vals[:n].view((n,) + self.ds.sample_shape), labs[:n].view(n)
+
+
+def ingest_chunks(store, name, chunks, first_row=0):
+    """Streaming ingest: fill a pre-`init`'d shard from an iterator of host arrays
+    (the reference's init + update-in-chunks pattern, include/ddstore.hpp:110-195) through a pinned double buffer,
+    so producing / reading chunk k+1 on the host overlaps the H2D copy of chunk k. Returns rows written."""
+    stream = torch.cuda.Stream()
+    pinned, events, k, row = [None, None], [None, None], 0, int(first_row)
+    for chunk in chunks:
+        arr = np.ascontiguousarray(chunk)
+        slot = k & 1
+        if events[slot] is not None:
+            events[slot].synchronize()  # the copy that used this pinned buffer two chunks ago is done
+        if pinned[slot] is None or pinned[slot].numel() < arr.nbytes:
+            pinned[slot] = torch.empty(max(arr.nbytes, 1), dtype=torch.uint8).pin_memory()
+        stage = pinned[slot][:arr.nbytes].numpy().view(arr.dtype).reshape(arr.shape)
+        stage[...] = arr
+        store.update(name, stage, row, stream=stream.cuda_stream, wait=False)  # bounds-checked H2D, no sync
+        events[slot] = torch.cuda.Event()
+        events[slot].record(stream)
+        row += arr.shape[0]
+        k += 1
+    stream.synchronize()
+    return row - int(first_row)

@@ -96,11 +96,16 @@ class PyDDStore:
     def init(self, name, nrows, disp, itemsize=1):
         _capi.raise_for(self._L.dds_init(self._h, name.encode(), int(nrows), int(disp), int(itemsize)))  # :112-113
 
-    def update(self, name, arr, offset):
-        # src/pyddstore.pyx:115-131
+    def update(self, name, arr, offset, stream=None, wait=True):
+        # src/pyddstore.pyx:115-131. wait=False: enqueue the copy on `stream` and return (streaming ingest; the
+        # source must stay valid -- pinned -- until the stream reaches it).
         b = _Buf(arr)
-        _capi.raise_for(self._L.dds_update(self._h, name.encode(), b.ptr, b.shape[0], int(offset), b.itemsize,
-                                           b.on_device))
+        if wait:
+            rc = self._L.dds_update(self._h, name.encode(), b.ptr, b.shape[0], int(offset), b.itemsize, b.on_device)
+        else:
+            rc = self._L.dds_update_async(self._h, name.encode(), b.ptr, b.shape[0], int(offset), b.itemsize,
+                                          b.on_device, self._stream_arg(stream))
+        _capi.raise_for(rc)
 
     # ---------------------------------------------------------------- the batched hot path
     def get_batch(self, name, starts, counts=None, out=None, count=None, offsets=None, stream=None, wait=True):

@@ -111,6 +111,10 @@ int dds_init(dds_store_t *s, const char *name, int64_t nrows, int disp, int item
  * DDS_ERR_ARG.) */
 int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
                int buffer_on_device);
+/* dds_update without the trailing synchronise, on `cuda_stream` (NULL: the store's stream): for streaming ingest of a
+ * pre-init'd shard from pinned chunks (the copy of chunk k overlaps the host producing chunk k+1). */
+int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
+                     int buffer_on_device, void *cuda_stream);
 /* template<T> void get(string name, long start, long count, T* buffer), ddstore.hpp:197-248. Fetches
  * count rows starting at GLOBAL row `start` (must lie within one owner) into `buffer` (host, or device). */
 int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int itemsize, void *buffer,

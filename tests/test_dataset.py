@@ -103,3 +103,58 @@ def test_ragged_dataset_config4_shape():
         return True
 
     assert all(_world(P, body))
+
+
+def test_prefetch_loader_matches_plain_loader():
+    import torch
+    from ddstore_b200.dataset import DistDataset, PrefetchLoader
+    from torch.utils.data.distributed import DistributedSampler
+    rng = np.random.default_rng(5)
+    N, P = 700, 2
+    images = rng.integers(0, 2**32, size=(N, 3, 4), dtype=np.uint32).view(np.float32)
+    labels = rng.integers(0, 10, size=N)
+    data = [(images[i], int(labels[i])) for i in range(N)]
+
+    def body(comm, r):
+        ds = DistDataset(data, "t", comm=comm, device=0)
+        sampler = DistributedSampler(ds, num_replicas=P, rank=r, shuffle=True, seed=1)
+        sampler.set_epoch(3)
+        order = np.array(list(iter(sampler)))
+        got_v, got_l = [], []
+        acc = torch.zeros((), device="cuda:0")
+        for vals, labs in PrefetchLoader(ds, sampler, batch_size=48):
+            acc = acc + torch.nan_to_num(vals).abs().sum()  # consumer work queued on the current stream
+            got_v.append(vals.clone())
+            got_l.append(labs.clone())
+        v = torch.cat(got_v).cpu().numpy()
+        lab = torch.cat(got_l).cpu().numpy()
+        assert v.tobytes() == images[order].tobytes() and np.array_equal(lab, labels[order])
+        ds.free()
+        return True
+
+    assert all(_world(P, body))
+
+
+def test_streaming_ingest_into_initialised_shard():
+    from ddstore_b200 import PyDDStore
+    from ddstore_b200.dataset import ingest_chunks
+    rng = np.random.default_rng(6)
+
+    def body(comm, r):
+        store = PyDDStore(comm, device=0)
+        nrows = 5000 + 100 * r
+        full = rng.integers(0, 2**32, size=(nrows, 24), dtype=np.uint32).view(np.float32)
+        store.init("z", nrows, 24, 4)
+        wrote = ingest_chunks(store, "z", (full[i:i + 777] for i in range(0, nrows, 777)))
+        assert wrote == nrows
+        first = ([0] + store.query("z")["lenlist"])[r]
+        back = np.zeros_like(full)
+        store.get("z", back, first)
+        assert back.tobytes() == full.tobytes()
+        with pytest.raises(ValueError):
+            store.update("z", np.zeros((2, 24), np.float32), nrows - 1)  # past the end of the local shard
+        store.free()
+        store.close()
+        return True
+
+    assert all(_world(2, body))
