@@ -146,12 +146,84 @@ __device__ __forceinline__ void report(unsigned long long *status, int64_t req, 
 // ------------------------------------------------------------------------------------------------
 // gather kernel
 // ------------------------------------------------------------------------------------------------
+// where request i's (start row, row count) comes from: explicit arrays, or a per-sample table indexed by ids[i]
+struct PlanSrc {
+    const int64_t *starts, *counts;       // explicit (ids == nullptr)
+    const int64_t *ids;                   // sample ids (SURVEY.md 8f rank 2: device-resident sample index)
+    const int64_t *tab_start, *tab_count; // [nsamples] row_start / row_count of every sample of this variable
+    int64_t nsamples;
+};
+
+// Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as three unrolled passes
+// (ids, then table rows, then arithmetic) so that the K independent -- and for the sample index, dependent
+// two-level -- global loads of a thread are all in flight together instead of one DRAM latency after another.
+template <int K>
+__device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &p, const int64_t (&idx)[K], int64_t nreq,
+                                          unsigned long long *status, uint64_t (&src)[K], int64_t (&nbytes)[K]) {
+    int64_t start[K], count[K];
+    bool live[K], badid[K];
+    if (p.ids) {
+        int64_t id[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            live[k] = idx[k] < nreq;
+            id[k] = live[k] ? p.ids[idx[k]] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            badid[k] = live[k] && (id[k] < 0 || id[k] >= p.nsamples);
+            const bool ok = live[k] && !badid[k];
+            start[k] = ok ? p.tab_start[id[k]] : 0;
+            count[k] = ok ? p.tab_count[id[k]] : 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            live[k] = idx[k] < nreq;
+            badid[k] = false;
+            start[k] = live[k] ? p.starts[idx[k]] : 0;
+            count[k] = live[k] ? p.counts[idx[k]] : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        src[k] = 0;
+        nbytes[k] = 0;
+        if (!live[k]) continue;
+        if (badid[k]) {
+            report(status, idx[k], DDSK_CODE_SAMPLE);
+            continue;
+        }
+        uint64_t s = 0;
+        const int code = dev_locate(var, start[k], count[k], &s);
+        if (code) {
+            report(status, idx[k], code);
+            continue;
+        }
+        src[k] = s;
+        nbytes[k] = count[k] * var.row_bytes;
+    }
+}
+
+__device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int64_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 struct GatherArgs {
     ddsk_var_t var;
     const int64_t *starts;   // FIXED: start row per request
     int64_t count;           // FIXED: rows per request
-    const uint64_t *req_src; // VAR: planned source address (0 = skip)
-    const int64_t *req_dst;  // VAR: [nreq+1] exclusive scan; req_dst[nreq] = total bytes
+    uint64_t *req_src; // VAR: planned source address (0 = skip)
+    int64_t *req_dst;  // VAR: [nreq+1] exclusive scan; req_dst[nreq] = total bytes
+    PlanSrc plan;      // VAR with fused_plan: where (start, count) of request i comes from
+    unsigned long long *tile_state; // VAR with fused_plan: one look-back word per 128-request tile
+    unsigned int epoch;             // tags tile_state words of THIS launch (no per-launch memset)
+    int fused_plan;
     int64_t nreq;
     char *dst;
     int64_t dst_cap;
@@ -341,6 +413,117 @@ __device__ __forceinline__ void drain_chunk(uint32_t sb, uint32_t a, char *d, ui
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused plan (variable counts): the lookup + checks + exclusive scan of request sizes run INSIDE the gather
+// launch. Warps take 128-request tiles by ticket; a tile's offset comes from a decoupled look-back over the
+// tiles before it (each lane polls one predecessor). Tiles are ticketed in running order, so a tile only ever
+// waits for tiles held by warps that are already running: no co-residency assumption, no deadlock.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_ITEMS = 4;
+constexpr int TILE_REQ = 32 * TILE_ITEMS;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// tile_state word: [63:42] epoch (22 bits) | [41:40] flag (1 = aggregate, 2 = inclusive prefix) | [39:0] bytes
+__device__ __forceinline__ unsigned long long tile_pack(unsigned int epoch, unsigned int flag, int64_t v) {
+    return ((unsigned long long)(epoch & 0x3FFFFFu) << 42) | ((unsigned long long)flag << 40) |
+           ((unsigned long long)v & 0xFFFFFFFFFFull);
+}
+
+__device__ __forceinline__ void plan_in_kernel(const GatherArgs &a, int lane) {
+    const int64_t ntiles = (a.nreq + TILE_REQ - 1) / TILE_REQ;
+    while (true) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.counters[2], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if ((int64_t)tile >= ntiles) break;
+        // lane owns TILE_ITEMS consecutive requests
+        int64_t idx[TILE_ITEMS], nb[TILE_ITEMS];
+        uint64_t sv[TILE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) idx[k] = (int64_t)tile * TILE_REQ + lane * TILE_ITEMS + k;
+        plan_many<TILE_ITEMS>(a.var, a.plan, idx, a.nreq, a.status, sv, nb);
+        int64_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) mine += nb[k];
+        const int64_t incl = warp_incl_scan(mine, lane);
+        const int64_t agg = __shfl_sync(0xffffffffu, incl, 31);
+        // publish the aggregate, then look back
+        if (lane == 0) st_release_u64(&a.tile_state[tile], tile_pack(a.epoch, tile == 0 ? 2u : 1u, agg));
+        int64_t excl = 0;
+        if (tile > 0) {
+            int64_t base = (int64_t)tile - 1;
+            while (true) {
+                const int64_t t = base - lane; // lane 0 polls the nearest predecessor
+                unsigned long long wv = tile_pack(a.epoch, 2u, 0);
+                if (t >= 0) {
+                    const uint64_t t0 = globaltimer_ns();
+                    do {
+                        wv = ld_acquire_u64(&a.tile_state[t]);
+                        if (globaltimer_ns() - t0 > 4000000000ull) { // never expected; do not hang the box
+                            report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                            __trap();
+                        }
+                    } while ((unsigned int)(wv >> 42) != (a.epoch & 0x3FFFFFu) || ((wv >> 40) & 3u) == 0);
+                }
+                const unsigned int flag = (unsigned int)((wv >> 40) & 3u);
+                const int64_t val = (int64_t)(wv & 0xFFFFFFFFFFull);
+                const unsigned inc = __ballot_sync(0xffffffffu, flag == 2u);
+                const int stop = inc ? __ffs(inc) - 1 : 31; // nearest tile that already knows its inclusive prefix
+                int64_t c = lane <= stop ? val : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                excl += c;
+                if (inc) break;
+                base -= 32;
+            }
+            if (lane == 0) st_release_u64(&a.tile_state[tile], tile_pack(a.epoch, 2u, excl + agg));
+        }
+        int64_t run = excl + incl - mine;
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            if (idx[k] < a.nreq) {
+                a.req_src[idx[k]] = sv[k];
+                a.req_dst[idx[k]] = run;
+                if (a.offsets_out) a.offsets_out[idx[k]] = run;
+                run += nb[k];
+            }
+        }
+        if ((int64_t)tile == ntiles - 1 && lane == 31) {
+            a.req_dst[a.nreq] = excl + agg;
+            if (a.offsets_out) a.offsets_out[a.nreq] = excl + agg;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            atomicAdd(&a.counters[3], 1u);
+        }
+    }
+    // every tile has an owner that is running; wait until all of them have written their part of the plan
+    if (lane == 0) {
+        const uint64_t t0 = globaltimer_ns();
+        while ((int64_t)ld_acquire_u32(&a.counters[3]) < ntiles) {
+            __nanosleep(200);
+            if (globaltimer_ns() - t0 > 4000000000ull) {
+                report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                __trap();
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <bool FIXED, int NW, int S, int CH>
 __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_constant__ GatherArgs a) {
     constexpr int STAGE = CH + 32; // room for the aligned superset of a misaligned CH-byte range
@@ -368,10 +551,12 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncwarp();
 
+    if (!FIXED && a.fused_plan) plan_in_kernel(a, lane);
+
     // ---- total bytes, segment geometry -------------------------------------------------------
     ChunkWalker<FIXED, CH> w;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
-    w.T = FIXED ? w.nb * a.nreq : a.req_dst[a.nreq];
+    w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
     bool over = w.T > a.dst_cap;
     {
         int64_t target = w.T / (nwarps * 8);
@@ -470,6 +655,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         if (done == (unsigned int)(nwarps - 1)) {
             a.counters[0] = 0;
             a.counters[1] = 0;
+            a.counters[2] = 0;
+            a.counters[3] = 0;
             __threadfence();
         }
     }
@@ -484,74 +671,6 @@ constexpr int PLAN_TILE = PLAN_THREADS * PLAN_ITEMS;
 constexpr int PLAN1_THREADS = 1024; // single-CTA plan for small batches
 constexpr int PLAN1_ITEMS = 8;
 constexpr int PLAN1_MAX = PLAN1_THREADS * PLAN1_ITEMS;
-
-// where request i's (start row, row count) comes from: explicit arrays, or a per-sample table indexed by ids[i]
-struct PlanSrc {
-    const int64_t *starts, *counts;       // explicit (ids == nullptr)
-    const int64_t *ids;                   // sample ids (SURVEY.md 8f rank 2: device-resident sample index)
-    const int64_t *tab_start, *tab_count; // [nsamples] row_start / row_count of every sample of this variable
-    int64_t nsamples;
-};
-
-// Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as three unrolled passes
-// (ids, then table rows, then arithmetic) so that the K independent -- and for the sample index, dependent
-// two-level -- global loads of a thread are all in flight together instead of one DRAM latency after another.
-template <int K>
-__device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &p, const int64_t (&idx)[K], int64_t nreq,
-                                          unsigned long long *status, uint64_t (&src)[K], int64_t (&nbytes)[K]) {
-    int64_t start[K], count[K];
-    bool live[K], badid[K];
-    if (p.ids) {
-        int64_t id[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            live[k] = idx[k] < nreq;
-            id[k] = live[k] ? p.ids[idx[k]] : 0;
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            badid[k] = live[k] && (id[k] < 0 || id[k] >= p.nsamples);
-            const bool ok = live[k] && !badid[k];
-            start[k] = ok ? p.tab_start[id[k]] : 0;
-            count[k] = ok ? p.tab_count[id[k]] : 0;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            live[k] = idx[k] < nreq;
-            badid[k] = false;
-            start[k] = live[k] ? p.starts[idx[k]] : 0;
-            count[k] = live[k] ? p.counts[idx[k]] : 0;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        src[k] = 0;
-        nbytes[k] = 0;
-        if (!live[k]) continue;
-        if (badid[k]) {
-            report(status, idx[k], DDSK_CODE_SAMPLE);
-            continue;
-        }
-        uint64_t s = 0;
-        const int code = dev_locate(var, start[k], count[k], &s);
-        if (code) {
-            report(status, idx[k], code);
-            continue;
-        }
-        src[k] = s;
-        nbytes[k] = count[k] * var.row_bytes;
-    }
-}
-
-__device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int64_t o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += o;
-    }
-    return v;
-}
 
 // block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, *total = block sum
 template <int NT>
@@ -709,6 +828,7 @@ bool g_geom_init = false;
 int g_sms = 0;
 int g_ctas_per_sm = 1;
 int g_pdl = 1;
+int g_fused_plan = 1; // DDS_FUSED_PLAN: 1 = auto (fused for <= 8192 requests), 0 = never, 2 = always (A/B switch)
 
 int pick_geometry() {
     if (g_geom_init) return 0;
@@ -722,6 +842,7 @@ int pick_geometry() {
     if (g_geom_var_env >= kNumGeoms) g_geom_var_env = -1;
     if (const char *e = getenv("DDS_GATHER_CTAS_PER_SM")) g_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
+    if (const char *e = getenv("DDS_FUSED_PLAN")) g_fused_plan = atoi(e);
     g_geom_init = true;
     return 0;
 }
@@ -840,7 +961,7 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
 }
 
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev, int64_t dst_capacity,
-                    int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status, void *stream) {
+                    int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int reset_status, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0) return 0;
@@ -857,20 +978,25 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
     p.tab_start = index->table_start;
     p.tab_count = index->table_count;
     p.nsamples = index->nsamples;
-    // one CTA is enough for explicit (start, count) arrays (coalesced loads); the sample-index lookups are random
-    // two-level gathers and want more SMs' worth of memory parallelism (measured: 1 CTA costs +25 us at B=4096)
-    if (nreq <= (p.ids ? (int64_t)PLAN_TILE : (int64_t)PLAN1_MAX)) {
-        if (int rc = launch_pdl(dds_plan_single_kernel, dim3(1), dim3(PLAN1_THREADS), st, *var, p, nreq, scr->req_src,
-                                scr->req_dst, offsets_dev_or_null, scr->status))
-            return rc;
-    } else {
-        const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
-        if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq, scr->req_src,
-                                scr->req_dst, scr->tile_sums, scr->status))
-            return rc;
-        if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
-                                (const int64_t *)scr->tile_sums, offsets_dev_or_null))
-            return rc;
+    // measured (profiles/r1_configs.md): the in-kernel plan wins below ~8K requests (one launch instead of two or
+    // three: B=4096 54 -> 48 us), separate plan kernels are ~2 % faster above (they overlap the previous gather's tail)
+    const bool fused = g_fused_plan == 1 ? nreq <= 8192 : g_fused_plan == 2;
+    if (!fused) {
+        // one CTA is enough for explicit (start, count) arrays (coalesced loads); the sample-index lookups are random
+        // two-level gathers and want more SMs' worth of memory parallelism (measured: 1 CTA costs +25 us at B=4096)
+        if (nreq <= (p.ids ? (int64_t)PLAN_TILE : (int64_t)PLAN1_MAX)) {
+            if (int rc = launch_pdl(dds_plan_single_kernel, dim3(1), dim3(PLAN1_THREADS), st, *var, p, nreq, scr->req_src,
+                                    scr->req_dst, offsets_dev_or_null, scr->status))
+                return rc;
+        } else {
+            const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
+            if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq,
+                                    scr->req_src, scr->req_dst, scr->tile_sums, scr->status))
+                return rc;
+            if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
+                                    (const int64_t *)scr->tile_sums, offsets_dev_or_null))
+                return rc;
+        }
     }
     GatherArgs a;
     memset(&a, 0, sizeof(a));
@@ -882,6 +1008,18 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
     a.dst_cap = dst_capacity;
     a.status = scr->status;
     a.counters = scr->counters;
+    if (fused) {
+        a.plan = p;
+        a.tile_state = (unsigned long long *)scr->tile_sums;
+        scr->epoch = (scr->epoch + 1) & 0x3FFFFFu;
+        if (scr->epoch == 0) { // 22-bit tag wrapped: clear the words so a stale tag can never look current
+            CUDA_TRY(cudaMemsetAsync(scr->tile_sums, 0, (size_t)(scr->cap_req / 128 + 2) * 8, st));
+            scr->epoch = 1;
+        }
+        a.epoch = scr->epoch;
+        a.fused_plan = 1;
+        a.offsets_out = offsets_dev_or_null;
+    }
     return launch_gather<false>(a, st);
 }
 

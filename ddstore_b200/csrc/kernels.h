@@ -37,8 +37,9 @@ typedef struct ddsk_scratch {
     unsigned int *counters;     /* 4 words: [0] segment ticket, [1] finished warps (self-resetting) */
     uint64_t *req_src;          /* [cap_req]   planned source address per request (0 = skip) */
     int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
-    int64_t *tile_sums;         /* [cap_req/PLAN_TILE + 1] */
+    int64_t *tile_sums;         /* [cap_req/128 + 2] tile sums (separate plan kernels) / look-back words (fused plan) */
     int64_t cap_req;
+    unsigned int epoch;         /* host-side launch counter tagging the look-back words (22 bits, 0 = never) */
 } ddsk_scratch_t;
 
 /* Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
@@ -58,7 +59,7 @@ typedef struct ddsk_index {
 
 /* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. */
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev,
-                    int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                    int64_t dst_capacity, int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int reset_status,
                     void *stream);
 
 /* Synthetic payload: element (global_row g, col c) = low itemsize bytes of

@@ -168,7 +168,8 @@ int ensure_scratch(dds_store *s, int64_t nreq) {
     s->scr.cap_req = 0;
     CU(cudaMalloc((void **)&s->scr.req_src, (size_t)cap * 8));
     CU(cudaMalloc((void **)&s->scr.req_dst, (size_t)(cap + 1) * 8));
-    CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+    CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 128 + 2) * 8));
+    CU(cudaMemset(s->scr.tile_sums, 0, (size_t)(cap / 128 + 2) * 8));
     s->scr.cap_req = cap;
     return DDS_OK;
 }

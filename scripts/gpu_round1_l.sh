@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_dataset.py -m gpu -x -q 2>&1 | tail -6
+for f in 1 0; do
+echo "== DDS_FUSED_PLAN=$f"
+DDS_FUSED_PLAN=$f timeout 600 python scripts/bench_configs.py --cases cfg3,cfg4 --steps 20 --warmup 3 2>&1 | grep -E "^\{|rror" | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('  ', d['case'][:62].ljust(62), d['payload_GBps'], d['ms_per_step'])
+    else: print(l.rstrip()[:200])"
+done
