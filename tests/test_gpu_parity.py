@@ -415,3 +415,46 @@ def test_sample_index_lookup_fused_in_the_launch(coracle):
         return True
 
     assert all(run_world(P, body))
+
+
+PLAN_SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from ddstore_b200 import PyDDStore
+from oracle.oracle import COracle
+from tests.helpers import random_valid_requests
+rng = np.random.default_rng(77)
+shard = rng.integers(0, 256, size=(60000, 3), dtype=np.uint8)
+store = PyDDStore(device=0)
+store.add("b", shard)
+for B in (300, 9000, 70000):
+    starts, counts = random_valid_requests(rng, [60000], B, max_count=30)
+    exp, exp_offs, bad, _ = COracle().get_batch([shard], starts, counts)
+    out = np.zeros(max(exp.size, 1), np.uint8)
+    offs = np.zeros(B + 1, np.int64)
+    assert store.get_batch("b", starts, counts, out=out, offsets=offs) == exp.size
+    assert out[:exp.size].tobytes() == exp.tobytes() and offs.tolist() == exp_offs.tolist(), B
+    starts[B // 2] = 60000  # first bad request in the middle
+    try:
+        store.get_batch("b", starts, counts, out=out)
+        raise SystemExit("no error raised")
+    except ValueError as e:
+        assert str(e) == "Invalid count on target" and store.last_bad_index == B // 2
+store.free(); store.close()
+print("plan-ok")
+"""
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_plan_variants_agree(tmp_path, mode):
+    """DDS_FUSED_PLAN=0 (separate plan kernels) and =2 (in-kernel plan at every size) against the oracle"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "plan_variant.py"
+    script.write_text(PLAN_SCRIPT.format(root=root))
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_FUSED_PLAN=mode), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "plan-ok" in r.stdout, r.stdout + r.stderr
