@@ -363,13 +363,33 @@ struct ChunkWalker {
     }
 };
 
-#define DDS_FUNNEL4(W0, W1, W2, W3, W4)              \
-    out.x = __funnelshift_r(W0, W1, bs8);            \
-    out.y = __funnelshift_r(W1, W2, bs8);            \
-    out.z = __funnelshift_r(W2, W3, bs8);            \
-    out.w = __funnelshift_r(W3, W4, bs8);
+// Re-phase loop: output vector j = staged bytes [q16 + 16j + 4*WS + bs, +16). Specialised on the word shift WS
+// (and on whether a sub-word byte shift is needed at all) so the loop body is branch-free: two aligned 128-bit
+// shared loads, at most four funnel shifts, one aligned 128-bit global store.
+template <int WS, bool BYTES>
+__device__ __forceinline__ void rephase_loop(uint32_t sbase, char *dv, uint32_t nv, uint32_t bs8, int lane) {
+#pragma unroll 4
+    for (uint32_t j = (uint32_t)lane; j < nv; j += 32) {
+        const uint4 lo = lds128(sbase + (j << 4));
+        const uint4 hi = lds128(sbase + (j << 4) + 16);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint4 out;
+        if (BYTES) {
+            out.x = __funnelshift_r(w[WS + 0], w[WS + 1], bs8);
+            out.y = __funnelshift_r(w[WS + 1], w[WS + 2], bs8);
+            out.z = __funnelshift_r(w[WS + 2], w[WS + 3], bs8);
+            out.w = __funnelshift_r(w[WS + 3], w[WS + 4], bs8);
+        } else { // 4-byte-aligned shift (float32 / int32 / int64 rows): pure word selection
+            out.x = w[WS + 0];
+            out.y = w[WS + 1];
+            out.z = w[WS + 2];
+            out.w = w[WS + 3];
+        }
+        stg128(dv + ((size_t)j << 4), out);
+    }
+}
 
-// Drain one staged chunk: payload byte k lives at shared address sb + a + k and goes to d[k].
+// Drain one staged piece: payload byte k lives at shared address sb + a + k and goes to d[k].
 template <int CH>
 __device__ __forceinline__ void drain_chunk(uint32_t sb, uint32_t a, char *d, uint32_t n, int lane) {
     uint32_t head = (16u - (uint32_t)((uint64_t)d & 15u)) & 15u;
@@ -386,23 +406,18 @@ __device__ __forceinline__ void drain_chunk(uint32_t sb, uint32_t a, char *d, ui
                 tma_store_1d(d + head, sb + s, nv << 4);
             }
         } else {
-            // re-phase through registers: two aligned 128-bit shared loads -> funnel shift -> aligned 128-bit store
-            const uint32_t q16 = s & ~15u;
-            const uint32_t ws = sh >> 2;
+            const uint32_t sbase = sb + (s & ~15u);
             const uint32_t bs8 = (sh & 3u) * 8u;
             char *dv = d + head;
-#pragma unroll 4
-            for (uint32_t j = (uint32_t)lane; j < nv; j += 32) {
-                uint4 lo = lds128(sb + q16 + (j << 4));
-                uint4 hi = lds128(sb + q16 + (j << 4) + 16);
-                uint4 out;
-                switch (ws) {
-                case 0: DDS_FUNNEL4(lo.x, lo.y, lo.z, lo.w, hi.x) break;
-                case 1: DDS_FUNNEL4(lo.y, lo.z, lo.w, hi.x, hi.y) break;
-                case 2: DDS_FUNNEL4(lo.z, lo.w, hi.x, hi.y, hi.z) break;
-                default: DDS_FUNNEL4(lo.w, hi.x, hi.y, hi.z, hi.w) break;
-                }
-                stg128(dv + ((size_t)j << 4), out);
+            switch ((sh >> 2) * 2u + (bs8 ? 1u : 0u)) { // warp-uniform
+            case 0: rephase_loop<0, false>(sbase, dv, nv, bs8, lane); break; // unreachable (sh == 0), kept for the table
+            case 1: rephase_loop<0, true>(sbase, dv, nv, bs8, lane); break;
+            case 2: rephase_loop<1, false>(sbase, dv, nv, bs8, lane); break;
+            case 3: rephase_loop<1, true>(sbase, dv, nv, bs8, lane); break;
+            case 4: rephase_loop<2, false>(sbase, dv, nv, bs8, lane); break;
+            case 5: rephase_loop<2, true>(sbase, dv, nv, bs8, lane); break;
+            case 6: rephase_loop<3, false>(sbase, dv, nv, bs8, lane); break;
+            default: rephase_loop<3, true>(sbase, dv, nv, bs8, lane); break;
             }
         }
     }
