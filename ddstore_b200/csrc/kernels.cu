@@ -230,6 +230,7 @@ struct GatherArgs {
     int64_t *offsets_out; // FIXED: optional [nreq+1]
     unsigned long long *status;
     unsigned int *counters;
+    unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
 };
 
 // One pipeline stage carries a GROUP of up to 32 pieces (one per lane): consecutive requests of the walk, or one
@@ -676,6 +677,12 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             a.counters[2] = 0;
             a.counters[3] = 0;
             __threadfence();
+            if (a.host_mirror) { // the last warp publishes status + total straight into pinned host memory: the host
+                                 // reads them after the stream sync, no D2H copy in the call
+                a.host_mirror[0] = *(volatile unsigned long long *)a.status;
+                a.host_mirror[1] = (unsigned long long)w.T;
+                __threadfence_system();
+            }
         }
     }
 }
@@ -962,7 +969,7 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
                       int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
                       void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (reset_status & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0) return 0;
     GatherArgs a;
     memset(&a, 0, sizeof(a));
@@ -975,13 +982,14 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
     a.offsets_out = offsets_dev_or_null;
     a.status = scr->status;
     a.counters = scr->counters;
+    a.host_mirror = reset_status & 2 ? scr->host_mirror : nullptr; // bit 1 of the flags word: mirror wanted
     return launch_gather<true>(a, st);
 }
 
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev, int64_t dst_capacity,
                     int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int reset_status, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (reset_status) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (reset_status & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0) return 0;
     if (nreq > scr->cap_req) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_var: scratch too small (%lld > %lld)", (long long)nreq,
@@ -1026,6 +1034,7 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
     a.dst_cap = dst_capacity;
     a.status = scr->status;
     a.counters = scr->counters;
+    a.host_mirror = reset_status & 2 ? scr->host_mirror : nullptr;
     if (fused) {
         a.plan = p;
         a.tile_state = (unsigned long long *)scr->tile_sums;

@@ -39,13 +39,17 @@ typedef struct ddsk_scratch {
     int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
     int64_t *tile_sums;         /* [cap_req/128 + 2] tile sums (separate plan kernels) / look-back words (fused plan) */
     int64_t cap_req;
+    unsigned long long *host_mirror; /* device alias of 2 pinned host words: status, packed total (written by the
+                                        last warp of every gather launch); NULL = not used */
     unsigned int epoch;         /* host-side launch counter tagging the look-back words (22 bits, 0 = never) */
 } ddsk_scratch_t;
 
-/* Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
+/* `flags` of both launchers: bit 0 = reset the status word first, bit 1 = have the kernel's last warp mirror status +
+ * total into scr->host_mirror (synchronous calls; costs ~2 us at the kernel's end, so async queues skip it).
+ * Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
  * One launch: validate + owner lookup + gather + pack. */
 int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,
-                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int flags,
                       void *stream);
 
 /* Where the (start row, row count) of request i comes from (all device pointers): explicit arrays, or -- when
@@ -59,7 +63,7 @@ typedef struct ddsk_index {
 
 /* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. */
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev,
-                    int64_t dst_capacity, int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int reset_status,
+                    int64_t dst_capacity, int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int flags,
                     void *stream);
 
 /* Synthetic payload: element (global_row g, col c) = low itemsize bytes of

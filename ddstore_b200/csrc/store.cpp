@@ -31,6 +31,9 @@
 
 namespace {
 
+constexpr int64_t kSmallIdx = 8;          // requests whose host indices are read zero-copy (measured: slower than an H2D copy from ~32 on)
+constexpr int64_t kSmallOut = 64 * 1024;  // host destinations up to this size are written zero-copy
+
 thread_local std::string g_err;
 
 const char *code_text(int code) {
@@ -138,6 +141,9 @@ struct dds_store {
     void *d_out = nullptr;
     int64_t out_cap = 0;
     unsigned long long *h_status = nullptr; // pinned: [0] status, [1] total bytes
+    // small-call fast path (the legacy one-get-per-sample loader): zero-copy pinned bounce buffers the kernel reads
+    // indices from / writes the payload to directly, so a small host-to-host call is one launch + one sync
+    char *h_small = nullptr, *d_small = nullptr; // kSmallIdx*16 bytes of indices + kSmallOut bytes of payload
     // pending async batch
     bool pending = false;
     cudaStream_t pending_stream = nullptr;
@@ -516,7 +522,10 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
               cudaMalloc((void **)&s->scr.counters, 16) == cudaSuccess &&
               cudaMemset(s->scr.counters, 0, 16) == cudaSuccess &&
               cudaMemset(s->scr.status, 0xFF, 8) == cudaSuccess &&
-              cudaMallocHost((void **)&s->h_status, 16) == cudaSuccess;
+              cudaHostAlloc((void **)&s->h_status, 16, cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer((void **)&s->scr.host_mirror, s->h_status, 0) == cudaSuccess &&
+              cudaHostAlloc((void **)&s->h_small, (size_t)(kSmallIdx * 16 + kSmallOut), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer((void **)&s->d_small, s->h_small, 0) == cudaSuccess;
     if (!ok) {
         cuda_fail(cudaGetLastError(), "dds_create: device setup");
         delete s;
@@ -616,7 +625,16 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
 
     // ---- indices to the device (8-16 B per request)
     const int64_t *d_starts = starts, *d_counts = counts;
-    if (!idx_dev) {
+    if (!idx_dev && nreq <= kSmallIdx) {
+        // few requests: the kernel reads the indices straight from pinned host memory (no H2D copy to wait for)
+        int64_t *hs = (int64_t *)s->h_small, *hc = hs + kSmallIdx;
+        memcpy(hs, starts, (size_t)nreq * 8);
+        d_starts = (const int64_t *)s->d_small;
+        if (!fixed && !by_sample) {
+            memcpy(hc, counts, (size_t)nreq * 8);
+            d_counts = (const int64_t *)s->d_small + kSmallIdx;
+        }
+    } else if (!idx_dev) {
         if (int rc = ensure_idx(s, nreq)) return rc;
         CU(cudaMemcpyAsync(s->d_starts, starts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
         d_starts = s->d_starts;
@@ -647,10 +665,16 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
     // ---- destination: the caller's device buffer, or the store's staging buffer for a host destination
     void *d_dst = dst;
     int64_t cap = dst_capacity;
+    bool small_out = false;
     if (!dst_dev) {
         int64_t need = upper >= 0 ? std::min(upper, dst_capacity) : dst_capacity;
-        if (int rc = ensure_out(s, std::max<int64_t>(need, 16))) return rc;
-        d_dst = s->d_out;
+        if (need <= kSmallOut) { // small result: the kernel writes it straight into pinned host memory
+            small_out = true;
+            d_dst = s->d_small + kSmallIdx * 16;
+        } else {
+            if (int rc = ensure_out(s, std::max<int64_t>(need, 16))) return rc;
+            d_dst = s->d_out;
+        }
         cap = need;
     }
     if (!d_dst && cap > 0) return fail(DDS_ERR_ARG, "null destination");
@@ -659,7 +683,7 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
     int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
     int krc;
     if (fixed) {
-        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
+        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, no_sync ? 0 : 2, st);
     } else {
         ddsk_index_t ix;
         memset(&ix, 0, sizeof(ix));
@@ -672,7 +696,7 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             ix.starts = d_starts;
             ix.counts = d_counts;
         }
-        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &s->scr, 0, st);
+        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &s->scr, no_sync ? 0 : 2, st);
     }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
@@ -683,12 +707,18 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
         s->pending_stream = st;
         return DDS_OK;
     }
-    CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
-    if (!fixed) CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[nreq], 8, cudaMemcpyDeviceToHost, st));
+    // status + total arrive in the pinned mirror words with the end of the kernel (no D2H copy)
 
     // ---- results back to a host destination
     if (!dst_dev) {
-        if (upper >= 0) {
+        if (dst_offsets && !fixed)
+            CU(cudaMemcpyAsync(dst_offsets, s->scr.req_dst, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (small_out) {
+            CU(cudaStreamSynchronize(st));
+            int64_t tot = fixed ? upper : (int64_t)s->h_status[1];
+            if (tot > cap) tot = cap;
+            if (tot > 0) memcpy(dst, s->h_small + kSmallIdx * 16, (size_t)tot); // pinned bounce -> the caller's buffer
+        } else if (upper >= 0) {
             if (cap > 0) CU(cudaMemcpyAsync(dst, d_dst, (size_t)cap, cudaMemcpyDeviceToHost, st));
         } else {
             CU(cudaStreamSynchronize(st)); // device-resident counts: the size is only known on the device
@@ -696,12 +726,8 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             if (s->h_status[0] == DDSK_STATUS_OK && tot > 0 && tot <= cap)
                 CU(cudaMemcpyAsync(dst, d_dst, (size_t)tot, cudaMemcpyDeviceToHost, st));
         }
-        if (dst_offsets) {
-            if (fixed)
-                for (int64_t i = 0; i <= nreq; i++) dst_offsets[i] = i * (fixed_count > 0 ? fixed_count * R : 0);
-            else
-                CU(cudaMemcpyAsync(dst_offsets, s->scr.req_dst, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
-        }
+        if (dst_offsets && fixed)
+            for (int64_t i = 0; i <= nreq; i++) dst_offsets[i] = i * (fixed_count > 0 ? fixed_count * R : 0);
     }
     CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = fixed ? upper : (int64_t)s->h_status[1];
@@ -770,6 +796,7 @@ int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
     s->pending = false;
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->pending_stream;
+    // queued launches skip the host mirror (it costs ~2 us at the end of every kernel): read the words back here
     CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
     if (s->pending_fixed_total < 0)
         CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[s->pending_nreq], 8, cudaMemcpyDeviceToHost, st));
@@ -878,6 +905,7 @@ void dds_destroy(dds_store_t *s) {
         if (s->d_counts) cudaFree(s->d_counts);
         if (s->d_out) cudaFree(s->d_out);
         if (s->h_status) cudaFreeHost(s->h_status);
+        if (s->h_small) cudaFreeHost(s->h_small);
         if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();

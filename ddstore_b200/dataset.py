@@ -276,3 +276,48 @@ def ingest_chunks(store, name, chunks, first_row=0):
         k += 1
     stream.synchronize()
     return row - int(first_row)
+
+
+class DeviceBatchSampler:
+    """Epoch shuffle with the indices resident on the device: the permutation of an epoch is EXACTLY
+    torch's DistributedSampler order (same generator seeding: seed + epoch, same padding / striding,
+    examples/vae/vae-ddp.py:216), computed once per epoch and moved to the GPU in one copy; batches are then
+    slices of that tensor, so the per-batch index H2D copy and its sync disappear from the step.
+
+        sampler = DeviceBatchSampler(len(ds), batch_size, rank, world_size, seed=0)
+        for epoch in range(E):
+            sampler.set_epoch(epoch)
+            for ids in sampler:                       # int64 CUDA tensor views
+                store.get_batch("x", ids, out=buf[:len(ids)], count=1)
+    """
+
+    def __init__(self, dataset_len, batch_size, rank=0, world_size=1, shuffle=True, seed=0, drop_last=False, device=None):
+        class _Len:
+            def __init__(self, n):
+                self.n = n
+
+            def __len__(self):
+                return self.n
+
+        self._ds = DistributedSampler(_Len(dataset_len), num_replicas=world_size, rank=rank, shuffle=shuffle, seed=seed,
+                                      drop_last=False)
+        self.batch_size, self.drop_last = batch_size, drop_last
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._ids = None
+        self.set_epoch(0)
+
+    def set_epoch(self, epoch):
+        self._ds.set_epoch(epoch)
+        order = torch.tensor(list(iter(self._ds)), dtype=torch.int64)
+        self._ids = order.to(self.device, non_blocking=False)
+
+    def __len__(self):
+        n = self._ids.numel()
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self._ids.numel()
+        for b0 in range(0, n, self.batch_size):
+            if self.drop_last and b0 + self.batch_size > n:
+                return
+            yield self._ids[b0:b0 + self.batch_size]

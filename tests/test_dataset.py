@@ -158,3 +158,23 @@ def test_streaming_ingest_into_initialised_shard():
         return True
 
     assert all(_world(2, body))
+
+
+def test_device_batch_sampler_equals_distributed_sampler():
+    import torch
+    from ddstore_b200.dataset import DeviceBatchSampler
+    from torch.utils.data.distributed import DistributedSampler
+
+    class L:
+        def __len__(self):
+            return 1003
+
+    for rank in range(3):
+        ref = DistributedSampler(L(), num_replicas=3, rank=rank, shuffle=True, seed=11)
+        dev = DeviceBatchSampler(1003, 64, rank=rank, world_size=3, seed=11, device="cuda:0")
+        for epoch in (0, 5):
+            ref.set_epoch(epoch)
+            dev.set_epoch(epoch)
+            got = torch.cat([b for b in dev]).cpu().tolist()
+            assert got == list(iter(ref)) and all(b.is_cuda for b in dev)
+            assert len(dev) == (len(got) + 63) // 64
