@@ -261,6 +261,8 @@ struct ChunkWalker {
             if (FIXED) {
                 uint64_t s = 0;
                 int code = dev_locate(a.var, a.starts[idx], a.count, &s);
+                if (code) report(a.status, idx, code); // the reference's two checks; every request with bytes to
+                                                       // fetch passes through some warp's window at least once
                 w_src = code ? 0 : s; // invalid request: keep its slot in the packed layout, copy nothing
                 w_dst = idx * nb;
                 w_n = nb;
@@ -591,15 +593,14 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         w.nseg = 0;
     }
 
-    // ---- FIXED: validation pass (the reference's two checks, for EVERY request, even zero-byte ones)
-    if (FIXED) {
+    // ---- FIXED with nothing to walk (count == 0, or the batch does not fit): run the reference's two checks here,
+    //      so an invalid request is still the error that gets reported
+    if (FIXED && (w.nb == 0 || over)) {
         for (int64_t i = gwarp * 32 + lane; i < a.nreq; i += nwarps * 32) {
             uint64_t s;
             int code = dev_locate(a.var, a.starts[i], a.count, &s);
             if (code) report(a.status, i, code);
-            if (a.offsets_out) a.offsets_out[i] = i * w.nb;
         }
-        if (a.offsets_out && gwarp == 0 && lane == 0) a.offsets_out[a.nreq] = w.T;
     }
 
     // ---- per-warp pipeline -------------------------------------------------------------------
@@ -666,6 +667,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     }
     if (lane == 0) bulk_wait_all();
     __syncwarp();
+    if (FIXED && a.offsets_out) { // arithmetic offsets, written off the critical path
+        for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
+    }
 
     // ---- self-resetting ticket counters ------------------------------------------------------
     if (lane == 0) {
