@@ -92,7 +92,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
@@ -246,6 +245,8 @@ template <bool FIXED, int CH>
 struct ChunkWalker {
     // warp-uniform state
     int64_t seg_pos = 0, seg_end = 0, T = 0, seg_bytes = 0, nseg = 0, nb = 0;
+    int64_t gwarp = 0, nwarps = 1; // this warp's global index / warps in the grid (first segment = gwarp)
+    bool first_claim = true;
     int64_t r = 0, win_base = -64;
     // per-lane window of 32 request descriptors
     uint64_t w_src = 0;
@@ -293,11 +294,19 @@ struct ChunkWalker {
     __device__ __forceinline__ uint32_t next_group(const GatherArgs &a, int lane, Piece &pc) {
         while (true) {
             if (seg_pos >= seg_end) {
-                unsigned int seg = 0;
-                if (lane == 0) seg = atomicAdd(&a.counters[0], 1u);
-                seg = __shfl_sync(0xffffffffu, seg, 0);
-                if ((int64_t)seg >= nseg) return 0;
-                seg_pos = (int64_t)seg * seg_bytes;
+                // the first segment of warp g is segment g (no ticket: spares ~1800 same-address atomics at the
+                // start of every launch); later ones come from the ticket counter, offset by the warp count
+                int64_t seg;
+                if (first_claim) {
+                    first_claim = false;
+                    seg = gwarp;
+                } else {
+                    unsigned int t = 0;
+                    if (lane == 0) t = atomicAdd(&a.counters[0], 1u);
+                    seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+                }
+                if (seg >= nseg) return 0;
+                seg_pos = seg * seg_bytes;
                 seg_end = min(T, seg_pos + seg_bytes);
                 r = FIXED ? seg_pos / nb : locate_var(a, seg_pos, lane);
             }
@@ -573,6 +582,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
 
     // ---- total bytes, segment geometry -------------------------------------------------------
     ChunkWalker<FIXED, CH> w;
+    w.gwarp = gwarp;
+    w.nwarps = nwarps;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
     bool over = w.T > a.dst_cap;
@@ -665,7 +676,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         __syncwarp();                 // all lanes are done reading the stage before it is refilled
         consumed++;
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>(); // the stages have been read out; the global writes complete with the grid
     __syncwarp();
     if (FIXED && a.offsets_out) { // arithmetic offsets, written off the critical path
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
