@@ -630,12 +630,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             }
             const uint32_t st = issued % S;
             const uint32_t bar = smem_u32(&full_bar[warp][st]);
-            if (lane == 0) {
-                // the stage's previous tenant was drained >= 2 drains ago; its bulk stores (if any) are at most
-                // the second most recent bulk group of this thread
-                bulk_wait_read<1>();
-                mbar_expect_tx(bar, total);
-            }
+            // the stage's previous tenant was drained >= 2 drains ago; the bulk stores a lane issued for it (if any)
+            // are at most that lane's second most recent bulk group
+            bulk_wait_read<1>();
+            if (lane == 0) mbar_expect_tx(bar, total);
             __syncwarp();
             const uint32_t al = (uint32_t)(pc.src & 15u);
             desc[warp][st][lane].dpos = pc.dpos;
@@ -663,7 +661,13 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         const int64_t my_dpos = desc[warp][st][lane].dpos;
         const uint32_t my_n = desc[warp][st][lane].n;
         const uint32_t my_pack = desc[warp][st][lane].pack;
-        unsigned todo = __ballot_sync(0xffffffffu, my_n != 0);
+        // Pieces whose staged bytes, destination and size are all 16-byte aligned (every piece of an aligned
+        // fixed-stride batch) are stored by their own lane, all lanes at once: one TMA bulk store each, no loop.
+        char *const my_dst = a.dst + my_dpos;
+        const bool direct = my_n != 0 && (((uint32_t)(uint64_t)my_dst | my_n | (my_pack >> 16)) & 15u) == 0;
+        if (direct) tma_store_1d(my_dst, ring + st * STAGE + (my_pack & 0xffffu), my_n);
+        // the rest (re-phase, or <16-byte heads/tails) is drained cooperatively, piece by piece
+        unsigned todo = __ballot_sync(0xffffffffu, my_n != 0 && !direct);
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -672,11 +676,11 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, j);
             drain_chunk<CH>(ring + st * STAGE + (pk & 0xffffu), pk >> 16, a.dst + dpos, n, lane);
         }
-        if (lane == 0) bulk_commit(); // one (possibly empty) bulk group per drained stage
-        __syncwarp();                 // all lanes are done reading the stage before it is refilled
+        bulk_commit(); // every lane: one (possibly empty) bulk group per drained stage
+        __syncwarp();  // all lanes are done reading the stage before it is refilled
         consumed++;
     }
-    if (lane == 0) bulk_wait_read<0>(); // the stages have been read out; the global writes complete with the grid
+    bulk_wait_read<0>(); // every lane: its stages have been read out; the global writes complete with the grid
     __syncwarp();
     if (FIXED && a.offsets_out) { // arithmetic offsets, written off the critical path
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
