@@ -431,6 +431,9 @@ def run_ours(args):
 
 def main():
     args = parse()
+    if not os.path.exists(os.path.join(ROOT, "ddstore_b200", "libddstore_b200.so")):
+        import __graft_entry__  # fresh checkout: build the native pieces in-tree first
+        __graft_entry__.build()
     if args.impl == "reference":
         run_reference(args)
     else:
