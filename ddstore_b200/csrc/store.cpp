@@ -330,6 +330,10 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
         int my_fd = v.block.fd >= 0 ? v.block.fd : 0;
         int xrc = dds_vmm::exchange_fds(s->comm, tag, my_fd, want, &fds);
         if (!map_rc) map_rc = xrc;
+        if (v.block.fd >= 0) { // every peer holds its own duplicate now; one descriptor per variable would add up
+            close(v.block.fd);
+            v.block.fd = -1;
+        }
     }
     for (int r = 0; r < s->size && !map_rc; r++) {
         const PeerRec &p = all[(size_t)r];
