@@ -458,3 +458,63 @@ def test_plan_variants_agree(tmp_path, mode):
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_FUSED_PLAN=mode), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "plan-ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_edge_cases_of_the_batch_entry(coracle):
+    """empty batches, zero counts, a million tiny requests (scratch growth), sticky-status re-arm after an error,
+    queued async batches reporting through wait()"""
+    torch = _torch()
+    rng = np.random.default_rng(31)
+    shards = [rng.integers(0, 256, size=(n, 6), dtype=np.uint8) for n in (500, 0, 700)]
+    ll = O.np_lenlist([500, 0, 700])
+
+    def body(store, r):
+        store.add("v", shards[r])
+        dev = torch.device("cuda", 0)
+        # nreq == 0
+        out = np.zeros(16, np.uint8)
+        offs = np.full(1, -1, np.int64)
+        assert store.get_batch("v", np.zeros(0, np.int64), np.zeros(0, np.int64), out=out, offsets=offs) == 0
+        assert offs[0] == 0
+        # every count zero (nothing to copy, but the range checks still run: start 1200 is out of range)
+        assert store.get_batch("v", [0, 499, 500, 1199], [0, 0, 0, 0], out=out) == 0
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.get_batch("v", [0, 1200], out=out, count=0)
+        assert store.last_bad_index == 1
+        # ... and the sticky status word is re-armed: the next valid call succeeds
+        exp, _, _, _ = coracle.get_batch(shards, [3, 600], [2, 2])
+        o2 = np.zeros(exp.size, np.uint8)
+        assert store.get_batch("v", [3, 600], out=o2, count=2) == exp.size and o2.tobytes() == exp.tobytes()
+        # fixed count > 1 with device offsets
+        st = np.array([0, 10, 498, 500, 1190], np.int64)
+        exp, exp_offs, bad, _ = coracle.get_batch(shards, st, [2] * 5)
+        d_out = torch.zeros(exp.size, dtype=torch.uint8, device=dev)
+        d_offs = torch.zeros(6, dtype=torch.int64, device=dev)
+        store.get_batch("v", torch.from_numpy(st).to(dev), out=d_out, count=2, offsets=d_offs)
+        assert d_out.cpu().numpy().tobytes() == exp.tobytes() and d_offs.cpu().tolist() == exp_offs.tolist()
+        # a million one-row requests (plan scratch grows, > 8192 -> separate plan kernels)
+        B = 1_000_000
+        starts, counts = random_valid_requests(rng, ll, B, max_count=1)
+        exp, exp_offs, bad, _ = coracle.get_batch(shards, starts, counts)
+        big = np.zeros(exp.size, np.uint8)
+        assert store.get_batch("v", starts, counts, out=big) == exp.size and big.tobytes() == exp.tobytes()
+        # queued async batches: the first error of the queue surfaces in wait(), then the store is usable again
+        ds, dc = torch.from_numpy(starts[:4096]).to(dev), torch.from_numpy(counts[:4096]).to(dev)
+        bad_s = ds.clone()
+        bad_s[77] = -5
+        dbuf = torch.zeros(4096 * 6, dtype=torch.uint8, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        store.get_batch("v", ds, dc, out=dbuf, stream=side.cuda_stream, wait=False)
+        store.get_batch("v", bad_s, dc, out=dbuf, stream=side.cuda_stream, wait=False)
+        store.get_batch("v", ds, dc, out=dbuf, stream=side.cuda_stream, wait=False)
+        with pytest.raises(ValueError, match="Invalid start on target"):
+            store.wait()
+        assert store.last_bad_index == 77
+        store.get_batch("v", ds, dc, out=dbuf, stream=side.cuda_stream, wait=False)
+        n = store.wait()
+        e4, _, _, _ = coracle.get_batch(shards, starts[:4096], counts[:4096])
+        assert n == e4.size and dbuf[:n].cpu().numpy().tobytes() == e4.tobytes()
+        return True
+
+    assert all(run_world(3, body))
