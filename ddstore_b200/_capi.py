@@ -14,7 +14,7 @@ DDS_OK = 0
 ERR_DTYPE, ERR_START, ERR_COUNT, ERR_DISP, ERR_FENCE_ACTIVE, ERR_FENCE_INACTIVE = 1, 2, 3, 4, 5, 6
 ERR_UNKNOWN_VAR, ERR_EXISTS, ERR_CUDA, ERR_COMM, ERR_ARG, ERR_CAPACITY, ERR_NO_DEVICE, ERR_WATCHDOG = \
     7, 8, 9, 10, 11, 12, 13, 14
-IDX_ON_DEVICE, DST_ON_DEVICE, NO_SYNC = 1, 2, 4
+IDX_ON_DEVICE, DST_ON_DEVICE, NO_SYNC, OVERLAP = 1, 2, 4, 8
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)

@@ -229,6 +229,9 @@ struct GatherArgs {
     int64_t *offsets_out; // FIXED: optional [nreq+1]
     unsigned long long *status;
     unsigned int *counters;
+    int overlap;   // FIXED, declared independent of its neighbours in the queue: touch no shared mutable state
+                   // (segments are strided statically instead of ticketed)
+    int skip_wait; // ... and the launch before it was one too: do not wait for it to finish
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
 };
 
@@ -246,7 +249,8 @@ struct ChunkWalker {
     // warp-uniform state
     int64_t seg_pos = 0, seg_end = 0, T = 0, seg_bytes = 0, nseg = 0, nb = 0;
     int64_t gwarp = 0, nwarps = 1; // this warp's global index / warps in the grid (first segment = gwarp)
-    bool first_claim = true;
+    bool first_claim = true, static_claims = false;
+    int64_t cur_seg = 0;
     int64_t r = 0, win_base = -64;
     // per-lane window of 32 request descriptors
     uint64_t w_src = 0;
@@ -300,11 +304,14 @@ struct ChunkWalker {
                 if (first_claim) {
                     first_claim = false;
                     seg = gwarp;
+                } else if (static_claims) {
+                    seg = cur_seg + nwarps; // overlapped launches share no mutable state: plain striding
                 } else {
                     unsigned int t = 0;
                     if (lane == 0) t = atomicAdd(&a.counters[0], 1u);
                     seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, t, 0);
                 }
+                cur_seg = seg;
                 if (seg >= nseg) return 0;
                 seg_pos = seg * seg_bytes;
                 seg_end = min(T, seg_pos + seg_bytes);
@@ -575,7 +582,12 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         fence_mbar_init();
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // An overlapped batch shares nothing with the launches before it (own destination, indices already in place,
+    // no ticket counters), so its CTAs start moving bytes as soon as an SM frees up: the tail of batch k and the
+    // head of batch k+1 overlap, whatever else is running on the GPU.
+    // (The first batch of such a run still waits, so a ticketed launch before the run has retired for good before
+    // any ticketed launch after the run can start.)
+    if (!(FIXED && a.skip_wait)) asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncwarp();
 
     if (!FIXED && a.fused_plan) plan_in_kernel(a, lane);
@@ -584,6 +596,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     ChunkWalker<FIXED, CH> w;
     w.gwarp = gwarp;
     w.nwarps = nwarps;
+    w.static_claims = FIXED && a.overlap;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
     bool over = w.T > a.dst_cap;
@@ -686,8 +699,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
     }
 
-    // ---- self-resetting ticket counters ------------------------------------------------------
-    if (lane == 0) {
+    // ---- self-resetting ticket counters (not used by overlapped launches) ---------------------
+    if (lane == 0 && !(FIXED && a.overlap)) {
         __threadfence();
         unsigned int done = atomicAdd(&a.counters[1], 1u);
         if (done == (unsigned int)(nwarps - 1)) {
@@ -1000,6 +1013,8 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
     a.dst_cap = dst_capacity;
     a.offsets_out = offsets_dev_or_null;
     a.status = scr->status;
+    a.overlap = (reset_status & 4) ? 1 : 0;    // bit 2: independent batch -> static segment striding
+    a.skip_wait = (reset_status & 16) ? 1 : 0; // bit 4: ... whose predecessor was one too -> no grid wait
     a.counters = scr->counters;
     a.host_mirror = reset_status & 2 ? scr->host_mirror : nullptr; // bit 1 of the flags word: mirror wanted
     return launch_gather<true>(a, st);

@@ -34,7 +34,8 @@ typedef struct ddsk_var {
 /* scratch a store owns for the batched path (all device memory) */
 typedef struct ddsk_scratch {
     unsigned long long *status; /* 1 word */
-    unsigned int *counters;     /* 4 words: [0] segment ticket, [1] finished warps (self-resetting) */
+    unsigned int *counters;     /* 4 words: [0] segment ticket, [1] finished warps, [2] plan ticket,
+                                   [3] finished plan tiles -- all self-resetting */
     uint64_t *req_src;          /* [cap_req]   planned source address per request (0 = skip) */
     int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
     int64_t *tile_sums;         /* [cap_req/128 + 2] tile sums (separate plan kernels) / look-back words (fused plan) */
@@ -45,7 +46,9 @@ typedef struct ddsk_scratch {
 } ddsk_scratch_t;
 
 /* `flags` of both launchers: bit 0 = reset the status word first, bit 1 = have the kernel's last warp mirror status +
- * total into scr->host_mirror (synchronous calls; costs ~2 us at the kernel's end, so async queues skip it).
+ * total into scr->host_mirror (synchronous calls; costs ~2 us at the kernel's end, so async queues skip it);
+ * fixed entry only: bit 2 = independent batch (static segment striding instead of the ticket counters: no shared
+ * mutable state), bit 4 = its predecessor in the queue was one too (skip griddepcontrol.wait: the two overlap).
  * Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
  * One launch: validate + owner lookup + gather + pack. */
 int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,

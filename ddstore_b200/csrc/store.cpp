@@ -149,6 +149,8 @@ struct dds_store {
     cudaStream_t pending_stream = nullptr;
     int64_t pending_fixed_total = -1;
     int64_t pending_nreq = 0;
+    bool prev_fixed = false;
+    bool prev_overlap = false; // the previous launch was a DDS_OVERLAP batch (then the next one may skip the grid wait)
 };
 
 namespace {
@@ -687,7 +689,13 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
     int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
     int krc;
     if (fixed) {
-        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr, no_sync ? 0 : 2, st);
+        // DDS_OVERLAP: declared independent of its neighbours in the queue. It never touches the ticket counters;
+        // it also skips the grid wait when the launch right before it (same stream) was one too.
+        const bool ovl = no_sync && (flags & DDS_OVERLAP);
+        const bool skip = ovl && chain && s->prev_overlap;
+        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr,
+                                (no_sync ? 0 : 2) | (ovl ? 4 : 0) | (skip ? 16 : 0), st);
+        s->prev_overlap = ovl;
     } else {
         ddsk_index_t ix;
         memset(&ix, 0, sizeof(ix));
@@ -701,11 +709,13 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             ix.counts = d_counts;
         }
         krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &s->scr, no_sync ? 0 : 2, st);
+        s->prev_overlap = false;
     }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
     s->pending_fixed_total = fixed ? upper : -1;
     s->pending_nreq = nreq;
+    s->prev_fixed = fixed;
     if (no_sync) { // nothing but the kernel(s) goes on the stream; the status word is read back in dds_batch_wait
         s->pending = true;
         s->pending_stream = st;

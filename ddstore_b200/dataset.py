@@ -225,8 +225,11 @@ class PrefetchLoader:
         with torch.cuda.stream(self.stream):
             d_idx[:n].copy_(host_idx, non_blocking=True)
             st = self.stream.cuda_stream
-            self.ds.ddstore.get_batch(f"{self.ds.label}data", d_idx[:n], out=vals[:n], count=1, stream=st, wait=False)
-            self.ds.ddstore.get_batch(f"{self.ds.label}labels", d_idx[:n], out=labs[:n], count=1, stream=st, wait=False)
+            # independent batches into alternating buffer sets: let consecutive launches overlap (DDS_OVERLAP)
+            self.ds.ddstore.get_batch(f"{self.ds.label}data", d_idx[:n], out=vals[:n], count=1, stream=st, wait=False,
+                                      overlap=True)
+            self.ds.ddstore.get_batch(f"{self.ds.label}labels", d_idx[:n], out=labs[:n], count=1, stream=st, wait=False,
+                                      overlap=True)
             self.events[slot].record(self.stream)
         return n, host_idx
 

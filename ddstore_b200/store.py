@@ -108,7 +108,8 @@ class PyDDStore:
         _capi.raise_for(rc)
 
     # ---------------------------------------------------------------- the batched hot path
-    def get_batch(self, name, starts, counts=None, out=None, count=None, offsets=None, stream=None, wait=True):
+    def get_batch(self, name, starts, counts=None, out=None, count=None, offsets=None, stream=None, wait=True,
+                  overlap=False):
         """Fetch len(starts) requests in ONE kernel launch, packed back to back in request order.
 
         starts/counts: int64 index arrays (host ndarray/list, or CUDA int64 tensors). counts=None means
@@ -119,6 +120,8 @@ class PyDDStore:
         (same residency as `out`). Returns the number of packed bytes.
         wait=False (device indices + device out only): enqueue on `stream` and return at once; call
         `wait()` later for the status. Several such batches may be queued on one stream.
+        overlap=True (with wait=False, fixed count): this batch is independent of the one queued just before it
+        (different `out`, indices not written by it) and may overlap with its tail -- double-buffered prefetch.
         Raises the reference's ValueError for the first invalid request (requests before it are delivered).
         """
         itemsize = self._itemsize.get(name)
@@ -142,7 +145,7 @@ class PyDDStore:
             keep = (sa, ca)
         flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | (_capi.DST_ON_DEVICE if ob.on_device else 0)
         if not wait:
-            flags |= _capi.NO_SYNC
+            flags |= _capi.NO_SYNC | (_capi.OVERLAP if overlap else 0)
         op = None
         if offsets is not None:
             fb = _Buf(offsets, writable=True)

@@ -518,3 +518,38 @@ def test_edge_cases_of_the_batch_entry(coracle):
         return True
 
     assert all(run_world(3, body))
+
+
+def test_overlapped_queue_of_independent_batches(coracle):
+    """DDS_OVERLAP: a double-buffered queue of fixed-count batches whose launches overlap (no grid wait, static
+    segment striding), mixed with ordinary ticketed launches; every buffer must hold exactly its last batch."""
+    torch = _torch()
+    rng = np.random.default_rng(91)
+    shard = rng.integers(0, 2**32, size=(200_000, 256), dtype=np.uint32).view(np.float32)  # 1 KiB rows, 205 MB
+
+    def body(store, r):
+        store.add("x", shard)
+        dev = torch.device("cuda", 0)
+        B = 40_000
+        side = torch.cuda.Stream(device=dev)
+        bufs = [torch.zeros((B, 256), dtype=torch.float32, device=dev) for _ in range(2)]
+        batches = [rng.integers(0, 200_000, size=B) for _ in range(9)]
+        d_idx = [torch.from_numpy(b).to(dev) for b in batches]
+        torch.cuda.synchronize()
+        for k, ids in enumerate(d_idx):
+            # batches 0-3 overlapped, 4 ordinary (ticketed, waits), 5-8 overlapped again
+            store.get_batch("x", ids, out=bufs[k & 1], count=1, stream=side.cuda_stream, wait=False, overlap=(k != 4))
+        store.wait()
+        for slot, k in ((0, 8), (1, 7)):
+            assert bufs[slot].cpu().numpy().tobytes() == shard[batches[k]].tobytes(), f"buffer {slot} != batch {k}"
+        # an invalid request inside an overlapped queue is still reported, with its index
+        bad = d_idx[0].clone()
+        bad[123] = 200_000
+        store.get_batch("x", d_idx[1], out=bufs[0], count=1, stream=side.cuda_stream, wait=False, overlap=True)
+        store.get_batch("x", bad, out=bufs[1], count=1, stream=side.cuda_stream, wait=False, overlap=True)
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.wait()
+        assert store.last_bad_index == 123
+        return True
+
+    assert all(run_world(1, body))
