@@ -209,6 +209,10 @@ class PrefetchLoader:
         self.events = [torch.cuda.Event() for _ in range(self.depth)]
 
     def _batches(self):
+        if isinstance(self.sampler, DeviceBatchSampler):
+            # the epoch's permutation already lives on the device: batches are tensor slices, nothing to copy
+            yield from self.sampler
+            return
         cur = []
         for i in self.sampler:
             cur.append(int(i))
@@ -221,17 +225,22 @@ class PrefetchLoader:
     def _issue(self, slot, idx):
         vals, labs, d_idx = self.bufs[slot]
         n = len(idx)
-        host_idx = torch.as_tensor(idx, dtype=torch.int64).pin_memory()
+        keep = idx
         with torch.cuda.stream(self.stream):
-            d_idx[:n].copy_(host_idx, non_blocking=True)
+            if torch.is_tensor(idx) and idx.is_cuda:
+                ids = idx
+            else:
+                keep = torch.as_tensor(idx, dtype=torch.int64).pin_memory()
+                d_idx[:n].copy_(keep, non_blocking=True)
+                ids = d_idx[:n]
             st = self.stream.cuda_stream
             # independent batches into alternating buffer sets: let consecutive launches overlap (DDS_OVERLAP)
-            self.ds.ddstore.get_batch(f"{self.ds.label}data", d_idx[:n], out=vals[:n], count=1, stream=st, wait=False,
+            self.ds.ddstore.get_batch(f"{self.ds.label}data", ids, out=vals[:n], count=1, stream=st, wait=False,
                                       overlap=True)
-            self.ds.ddstore.get_batch(f"{self.ds.label}labels", d_idx[:n], out=labs[:n], count=1, stream=st, wait=False,
+            self.ds.ddstore.get_batch(f"{self.ds.label}labels", ids, out=labs[:n], count=1, stream=st, wait=False,
                                       overlap=True)
             self.events[slot].record(self.stream)
-        return n, host_idx
+        return n, keep
 
     def __iter__(self):
         consumer = torch.cuda.current_stream(self.ds.device)

@@ -129,6 +129,12 @@ def test_prefetch_loader_matches_plain_loader():
         v = torch.cat(got_v).cpu().numpy()
         lab = torch.cat(got_l).cpu().numpy()
         assert v.tobytes() == images[order].tobytes() and np.array_equal(lab, labels[order])
+        # the same epoch through a device-resident sampler: no per-batch index copy at all
+        from ddstore_b200.dataset import DeviceBatchSampler
+        dsamp = DeviceBatchSampler(len(ds), 48, rank=r, world_size=P, seed=1, device="cuda:0")
+        dsamp.set_epoch(3)
+        got2 = torch.cat([vals.clone() for vals, _ in PrefetchLoader(ds, dsamp, batch_size=48)]).cpu().numpy()
+        assert got2.tobytes() == images[order].tobytes()
         ds.free()
         return True
 
