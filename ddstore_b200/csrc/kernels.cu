@@ -3,27 +3,34 @@
 // What the reference does per sample (include/ddstore.hpp:197-238 + src/ddstore.cxx:5-17):
 //   owner = sortedsearch(lenlist, start); offset = lenlist[owner-1] (or 0); two range checks;
 //   MPI_Get of count*disp*itemsize bytes from the owner's window at row (start-offset).
-// What this file does per BATCH, in one persistent kernel:
+// What this file does per BATCH, in one persistent kernel (dds_gather_kernel):
 //   the same lookup + checks for every request, then a gather of all payloads from the owners'
-//   HBM shards (local, or peer-mapped over NVLink/NVSwitch via CUDA IPC) packed back to back into
-//   one contiguous device buffer.
+//   HBM shards (local, or peer-mapped over NVLink/NVSwitch -- CUDA VMM blocks shared by file
+//   descriptor, see vmm.cpp) packed back to back into one contiguous device buffer.
 //
 // Kernel design (bandwidth-bound byte mover, no tensor cores):
 //   * The packed destination byte range [0, T) is cut into segments that warps claim dynamically
-//     (one atomic per segment), so load balance is by BYTES, not by request count (lengths differ
-//     100x in the variable-length configs) and not by owner (remote rows are slower than local).
-//   * Every warp is an autonomous pipeline with a private ring of S shared-memory stages.
-//     Lane 0 issues one 1-D TMA bulk load (cp.async.bulk global->shared, mbarrier complete_tx)
-//     per chunk of <= CH payload bytes, S-1 chunks ahead. Loads are issued on the 16-byte-aligned
-//     superset of the source range, so arbitrary element alignment (4-byte floats, single bytes)
-//     is legal for TMA.
-//   * Drain, by destination alignment relative to the staged bytes:
-//       - same 16-byte phase  -> lane 0 issues one TMA bulk store shared->global for the body;
-//       - different phase     -> all lanes read two aligned 16-byte vectors from shared memory,
-//                                funnel-shift them into place and issue aligned 128-bit stores;
-//       - <16-byte head/tail  -> single byte stores by the first lanes.
+//     (one atomic per segment; statically strided for DDS_OVERLAP launches), so load balance is by
+//     BYTES, not by request count (lengths differ 100x in the variable-length configs) and not by
+//     owner (remote rows are slower than local).
+//   * Every warp is an autonomous pipeline with a private ring of S shared-memory stages. A stage
+//     carries a GROUP of up to 32 pieces, one per lane (consecutive small requests, or one <= CH-byte
+//     piece of a large one); every lane issues the 1-D TMA bulk load of its own piece
+//     (cp.async.bulk global->shared, mbarrier complete_tx), S-1 stages ahead, on the
+//     16-byte-aligned superset of the source range, so arbitrary element alignment (4-byte
+//     floats, single bytes) is legal for TMA.
+//   * Drain, per piece:
+//       - staged bytes, destination, size all 16-byte aligned -> the piece's own lane issues one
+//         TMA bulk store shared->global, all lanes at once;
+//       - same 16-byte phase, ragged ends -> lane 0 bulk-stores the body, byte stores for head/tail;
+//       - different phase -> all lanes read two aligned 16-byte vectors from shared memory,
+//         funnel-shift (or word-select) them into place and issue aligned 128-bit stores.
 //   * Request offsets in the packed buffer are an exclusive prefix sum of request sizes: arithmetic
-//     in the fixed-count entry; a block/warp-shuffle scan in the plan kernels for variable counts.
+//     in the fixed-count entry; for variable counts a warp-shuffle scan with decoupled look-back
+//     INSIDE the gather launch (<= 8192 requests) or in two small plan kernels before it. The
+//     (start, count) of a request may come from a device-resident per-sample index (sample ids in).
+//   * Launches carry the programmatic-dependent-launch attribute; independent batches
+//     (DDS_OVERLAP) skip the grid wait and overlap head-to-tail.
 //
 // Nothing here calls a library kernel; everything is launched from the ddsk_* functions at the end.
 #include <cuda_runtime.h>
