@@ -54,6 +54,9 @@ SIGNATURES = {
     "dds_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
     "dds_get_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_uint, C.c_void_p, I64P, I64P]),
+    "dds_get_samples_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_void_p), I64P, C.POINTER(C.c_void_p), C.c_uint, C.c_void_p, I64P,
+                                        I64P]),
     "dds_batch_wait": (C.c_int, [C.c_void_p, I64P, I64P]),
     "dds_set_sample_index": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "dds_get_samples": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,

@@ -158,6 +158,13 @@ struct PlanSrc {
     const int64_t *ids;                   // sample ids (device-resident sample index)
     const int64_t *tab_start, *tab_count; // [nsamples] row_start / row_count of every sample of this variable
     int64_t nsamples;
+    // multi-array batches (config 4: node_feat + edge_index of the same samples in ONE launch): request i belongs to
+    // variable i / per_var and to sample ids[i % per_var]; every variable has its own window and sample index
+    int nvars;                                   // 0/1: single variable
+    int64_t per_var;                             // requests per variable (= number of sample ids)
+    const ddsk_var_t *mvars;                     // [nvars] windows, device memory
+    const int64_t *mtab_start[DDSK_MAX_MULTI], *mtab_count[DDSK_MAX_MULTI];
+    int64_t mnsamples[DDSK_MAX_MULTI];
 };
 
 // Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as three unrolled passes
@@ -168,12 +175,31 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
                                           unsigned long long *status, uint64_t (&src)[K], int64_t (&nbytes)[K]) {
     int64_t start[K], count[K];
     bool live[K], badid[K];
-    if (p.ids) {
+    const ddsk_var_t *vp[K];
+    if (p.nvars > 1) {
+        int64_t id[K];
+        int v[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            live[k] = idx[k] < nreq;
+            v[k] = live[k] ? (int)(idx[k] / p.per_var) : 0;
+            id[k] = live[k] ? p.ids[idx[k] - (int64_t)v[k] * p.per_var] : 0;
+            vp[k] = &p.mvars[v[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            badid[k] = live[k] && (id[k] < 0 || id[k] >= p.mnsamples[v[k]]);
+            const bool ok = live[k] && !badid[k];
+            start[k] = ok ? p.mtab_start[v[k]][id[k]] : 0;
+            count[k] = ok ? p.mtab_count[v[k]][id[k]] : 0;
+        }
+    } else if (p.ids) {
         int64_t id[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
             live[k] = idx[k] < nreq;
             id[k] = live[k] ? p.ids[idx[k]] : 0;
+            vp[k] = &var;
         }
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -189,6 +215,7 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
             badid[k] = false;
             start[k] = live[k] ? p.starts[idx[k]] : 0;
             count[k] = live[k] ? p.counts[idx[k]] : 0;
+            vp[k] = &var;
         }
     }
 #pragma unroll
@@ -201,13 +228,13 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
             continue;
         }
         uint64_t s = 0;
-        const int code = dev_locate(var, start[k], count[k], &s);
+        const int code = dev_locate(*vp[k], start[k], count[k], &s);
         if (code) {
             report(status, idx[k], code);
             continue;
         }
         src[k] = s;
-        nbytes[k] = count[k] * var.row_bytes;
+        nbytes[k] = count[k] * vp[k]->row_bytes;
     }
 }
 
@@ -236,6 +263,10 @@ struct GatherArgs {
     int64_t *offsets_out; // FIXED: optional [nreq+1]
     unsigned long long *status;
     unsigned int *counters;
+    // multi-array batches (plan.nvars > 1): the packed result of variable v goes to mdst[v]
+    char *mdst[DDSK_MAX_MULTI];
+    int64_t mcap[DDSK_MAX_MULTI];
+    int64_t *moffsets[DDSK_MAX_MULTI]; // optional per-variable [per_var + 1] byte offsets
     int overlap;   // FIXED, declared independent of its neighbours in the queue: touch no shared mutable state
                    // (segments are strided statically instead of ticketed)
     int skip_wait; // ... and the launch before it was one too: do not wait for it to finish
@@ -607,6 +638,36 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
     bool over = w.T > a.dst_cap;
+    // multi-array batch: the walk runs over the concatenation of the variables' packed results; vbase[v] is where
+    // variable v starts in that virtual space (unused slots are +inf so dst_of() never selects them)
+    const bool multi = !FIXED && a.plan.nvars > 1;
+    int64_t vbase[DDSK_MAX_MULTI + 1];
+#pragma unroll
+    for (int v = 0; v <= DDSK_MAX_MULTI; v++) vbase[v] = INT64_MAX;
+    if (multi) {
+        over = false;
+#pragma unroll
+        for (int v = 0; v < DDSK_MAX_MULTI; v++)
+            if (v < a.plan.nvars) vbase[v] = *(volatile const int64_t *)&a.req_dst[(int64_t)v * a.plan.per_var];
+#pragma unroll
+        for (int v = 0; v < DDSK_MAX_MULTI; v++)
+            if (v < a.plan.nvars) {
+                const int64_t endv = v + 1 < a.plan.nvars ? vbase[v + 1] : w.T;
+                over |= endv - vbase[v] > a.mcap[v];
+            }
+    }
+    auto dst_of = [&](int64_t dpos) -> char * {
+        if (!multi) return a.dst + dpos;
+        int64_t b = vbase[0]; // static indices only: the tables stay in registers / the constant bank
+        char *d = a.mdst[0];
+#pragma unroll
+        for (int k = 1; k < DDSK_MAX_MULTI; k++)
+            if (dpos >= vbase[k]) {
+                b = vbase[k];
+                d = a.mdst[k];
+            }
+        return d + (dpos - b);
+    };
     {
         // FIXED: a claim is one atomic + a division, so small segments (8 per warp) keep the tail short.
         // VAR: every claim also costs a 32-ary search over req_dst (2-3 dependent L2 round trips), so segments are
@@ -683,7 +744,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         const uint32_t my_pack = desc[warp][st][lane].pack;
         // Pieces whose staged bytes, destination and size are all 16-byte aligned (every piece of an aligned
         // fixed-stride batch) are stored by their own lane, all lanes at once: one TMA bulk store each, no loop.
-        char *const my_dst = a.dst + my_dpos;
+        char *const my_dst = dst_of(my_dpos);
         const bool direct = my_n != 0 && (((uint32_t)(uint64_t)my_dst | my_n | (my_pack >> 16)) & 15u) == 0;
         if (direct) tma_store_1d(my_dst, ring + st * STAGE + (my_pack & 0xffffu), my_n);
         // the rest (re-phase, or <16-byte heads/tails) is drained cooperatively, piece by piece
@@ -694,7 +755,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             const int64_t dpos = __shfl_sync(0xffffffffu, my_dpos, j);
             const uint32_t n = __shfl_sync(0xffffffffu, my_n, j);
             const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, j);
-            drain_chunk<CH>(ring + st * STAGE + (pk & 0xffffu), pk >> 16, a.dst + dpos, n, lane);
+            drain_chunk<CH>(ring + st * STAGE + (pk & 0xffffu), pk >> 16, dst_of(dpos), n, lane);
         }
         bulk_commit(); // every lane: one (possibly empty) bulk group per drained stage
         __syncwarp();  // all lanes are done reading the stage before it is refilled
@@ -702,6 +763,17 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     }
     bulk_wait_read<0>(); // every lane: its stages have been read out; the global writes complete with the grid
     __syncwarp();
+    if (multi) { // per-variable byte offsets = plan offsets rebased to the variable's start
+        for (int64_t i = gwarp * 32 + lane; i < a.nreq + a.plan.nvars; i += nwarps * 32) {
+            // entry (v, j) for j in [0, per_var]: i enumerates nvars * (per_var + 1) slots
+            const int v = (int)(i / (a.plan.per_var + 1));
+            const int64_t j = i - (int64_t)v * (a.plan.per_var + 1);
+            if (v < a.plan.nvars && a.moffsets[v]) {
+                const int64_t basev = a.req_dst[(int64_t)v * a.plan.per_var]; // == vbase[v]; read from memory so that
+                a.moffsets[v][j] = a.req_dst[(int64_t)v * a.plan.per_var + j] - basev; // vbase[] is never indexed dynamically
+            }
+        }
+    }
     if (FIXED && a.offsets_out) { // arithmetic offsets, written off the critical path
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
     }
@@ -1039,6 +1111,7 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
     }
     if (int rc = pick_geometry()) return rc;
     PlanSrc p;
+    memset(&p, 0, sizeof(p));
     p.starts = index->starts;
     p.counts = index->counts;
     p.ids = index->sample_ids;
@@ -1087,6 +1160,74 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
         a.epoch = scr->epoch;
         a.fused_plan = 1;
         a.offsets_out = offsets_dev_or_null;
+    }
+    return launch_gather<false>(a, st);
+}
+
+int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int64_t nreq, ddsk_scratch_t *scr, int flags,
+                      void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flags & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (nreq <= 0 || m->nvars <= 0) return 0;
+    if (m->nvars > DDSK_MAX_MULTI) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_multi: more than %d variables", DDSK_MAX_MULTI);
+        return -2;
+    }
+    const int64_t total_req = nreq * m->nvars;
+    if (total_req > scr->cap_req) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_multi: scratch too small (%lld > %lld)", (long long)total_req,
+                 (long long)scr->cap_req);
+        return -2;
+    }
+    if (int rc = pick_geometry()) return rc;
+    PlanSrc p;
+    memset(&p, 0, sizeof(p));
+    p.ids = sample_ids_dev;
+    p.nvars = m->nvars;
+    p.per_var = nreq;
+    p.mvars = m->vars_dev;
+    for (int v = 0; v < m->nvars; v++) {
+        p.mtab_start[v] = m->table_start[v];
+        p.mtab_count[v] = m->table_count[v];
+        p.mnsamples[v] = m->nsamples[v];
+    }
+    ddsk_var_t dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    const bool fused = g_fused_plan == 1 ? total_req <= 8192 : g_fused_plan == 2;
+    if (!fused) {
+        const int tiles = (int)((total_req + PLAN_TILE - 1) / PLAN_TILE);
+        if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, dummy, p, total_req,
+                                scr->req_src, scr->req_dst, scr->tile_sums, scr->status))
+            return rc;
+        if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, total_req, scr->req_dst,
+                                (const int64_t *)scr->tile_sums, (int64_t *)nullptr))
+            return rc;
+    }
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.req_src = scr->req_src;
+    a.req_dst = scr->req_dst;
+    a.nreq = total_req;
+    a.dst = nullptr;
+    a.dst_cap = INT64_MAX;
+    a.status = scr->status;
+    a.counters = scr->counters;
+    a.host_mirror = flags & 2 ? scr->host_mirror : nullptr;
+    a.plan = p; // the gather needs nvars / per_var even when the plan ran in its own kernels
+    for (int v = 0; v < m->nvars; v++) {
+        a.mdst[v] = (char *)m->dst[v];
+        a.mcap[v] = m->cap[v];
+        a.moffsets[v] = m->offsets[v];
+    }
+    if (fused) {
+        a.tile_state = (unsigned long long *)scr->tile_sums;
+        scr->epoch = (scr->epoch + 1) & 0x3FFFFFu;
+        if (scr->epoch == 0) {
+            CUDA_TRY(cudaMemsetAsync(scr->tile_sums, 0, (size_t)(scr->cap_req / 128 + 2) * 8, st));
+            scr->epoch = 1;
+        }
+        a.epoch = scr->epoch;
+        a.fused_plan = 1;
     }
     return launch_gather<false>(a, st);
 }

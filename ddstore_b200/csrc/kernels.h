@@ -11,6 +11,7 @@ extern "C" {
 #endif
 
 #define DDSK_MAX_RANKS 64
+#define DDSK_MAX_MULTI 4 /* variables per multi-array launch */
 
 /* Device-visible description of one variable: what the reference keeps in VarInfo
  * (/root/reference/include/ddstore.hpp:10-22) minus the MPI window, plus the peer-mapped shard base
@@ -68,6 +69,21 @@ typedef struct ddsk_index {
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev,
                     int64_t dst_capacity, int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int flags,
                     void *stream);
+
+/* Multi-array batch: the rows of the SAME nreq sample ids in nvars (<= DDSK_MAX_MULTI) variables, one launch. vars_dev =
+ * device array of the variables' windows; table_*[v] = sample index of variable v; dst[v]/cap[v]/offsets[v] per variable
+ * (offsets[v] nullable, nreq+1 entries). On return of the stream, totals are req_dst-derived (see store.cpp). */
+typedef struct ddsk_multi {
+    int nvars;
+    const ddsk_var_t *vars_dev;
+    const int64_t *table_start[DDSK_MAX_MULTI], *table_count[DDSK_MAX_MULTI];
+    int64_t nsamples[DDSK_MAX_MULTI];
+    void *dst[DDSK_MAX_MULTI];
+    int64_t cap[DDSK_MAX_MULTI];
+    int64_t *offsets[DDSK_MAX_MULTI];
+} ddsk_multi_t;
+int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int64_t nreq, ddsk_scratch_t *scr, int flags,
+                      void *stream);
 
 /* Synthetic payload: element (global_row g, col c) = low itemsize bytes of
  * splitmix64(seed ^ (g*disp + c)). Bench / test helper, fills a local shard in place. */

@@ -149,6 +149,8 @@ struct dds_store {
     cudaStream_t pending_stream = nullptr;
     int64_t pending_fixed_total = -1;
     int64_t pending_nreq = 0;
+    ddsk_var_t *d_multi_vars = nullptr; // device copy of the windows of the last multi-array combination
+    std::string multi_key;
     bool prev_fixed = false;
     bool prev_overlap = false; // the previous launch was a DDS_OVERLAP batch (then the next one may skip the grid wait)
 };
@@ -803,6 +805,85 @@ int dds_get_samples(dds_store_t *s, const char *name, const int64_t *sample_ids,
                       total_bytes, bad_index);
 }
 
+int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, const int64_t *sample_ids, int64_t nreq,
+                          void *const *dsts, const int64_t *dst_capacities, int64_t *const *dst_offsets, unsigned flags,
+                          void *cuda_stream, int64_t *total_bytes, int64_t *bad_index) {
+    clear_error();
+    if (bad_index) *bad_index = -1;
+    if (!s || !names || !dsts || !dst_capacities) return fail(DDS_ERR_ARG, "null argument");
+    if (nvars < 1 || nvars > DDSK_MAX_MULTI) return fail(DDS_ERR_ARG, "1..4 variables per multi-array batch");
+    if (!(flags & DDS_DST_ON_DEVICE)) return fail(DDS_ERR_ARG, "multi-array batches deliver into device buffers");
+    if (nreq < 0 || (nreq > 0 && !sample_ids)) return fail(DDS_ERR_ARG, "bad sample ids");
+    Var *vv[DDSK_MAX_MULTI];
+    std::string key;
+    for (int v = 0; v < nvars; v++) {
+        vv[v] = find_var(s, names[v]);
+        if (!vv[v]) return fail(DDS_ERR_UNKNOWN_VAR, names[v] ? names[v] : "(null)");
+        if (!vv[v]->d_tab_start) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
+        key += vv[v]->name;
+        key += '\n';
+    }
+    const bool idx_dev = flags & DDS_IDX_ON_DEVICE, no_sync = flags & DDS_NO_SYNC;
+    if (no_sync && !idx_dev) return fail(DDS_ERR_ARG, "async batches need device indices and a device destination");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    const bool chain = s->pending && no_sync && st == s->pending_stream;
+    if (s->pending && !chain) {
+        if (int rc = dds_batch_wait(s, nullptr, nullptr)) return rc;
+    }
+    if (total_bytes)
+        for (int v = 0; v < nvars; v++) total_bytes[v] = 0;
+    if (nreq == 0) return DDS_OK;
+    if (key != s->multi_key) { // (re)build the device array of windows for this combination of variables
+        if (!s->d_multi_vars) CU(cudaMalloc((void **)&s->d_multi_vars, sizeof(ddsk_var_t) * DDSK_MAX_MULTI));
+        CU(cudaStreamSynchronize(st)); // nothing in flight may still read the previous combination
+        for (int v = 0; v < nvars; v++)
+            CU(cudaMemcpy(&s->d_multi_vars[v], &vv[v]->kv, sizeof(ddsk_var_t), cudaMemcpyHostToDevice));
+        s->multi_key = key;
+    }
+    const int64_t *d_ids = sample_ids;
+    if (!idx_dev) {
+        if (int rc = ensure_idx(s, nreq)) return rc;
+        CU(cudaMemcpyAsync(s->d_starts, sample_ids, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
+        d_ids = s->d_starts;
+    }
+    if (int rc = ensure_scratch(s, nreq * nvars)) return rc;
+    ddsk_multi_t m;
+    memset(&m, 0, sizeof(m));
+    m.nvars = nvars;
+    m.vars_dev = s->d_multi_vars;
+    for (int v = 0; v < nvars; v++) {
+        m.table_start[v] = vv[v]->d_tab_start;
+        m.table_count[v] = vv[v]->d_tab_count;
+        m.nsamples[v] = vv[v]->nsamples;
+        m.dst[v] = dsts[v];
+        m.cap[v] = dst_capacities[v];
+        m.offsets[v] = dst_offsets ? dst_offsets[v] : nullptr;
+    }
+    if (ddsk_gather_multi(&m, d_ids, nreq, &s->scr, no_sync ? 0 : 2, st)) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    s->prev_overlap = false;
+    s->prev_fixed = false;
+    s->pending_fixed_total = -1;
+    s->pending_nreq = nreq * nvars;
+    if (no_sync) {
+        s->pending = true;
+        s->pending_stream = st;
+        return DDS_OK;
+    }
+    // per-variable totals = differences of the plan offsets at the variable boundaries
+    int64_t *hb = (int64_t *)s->h_small;
+    for (int v = 1; v < nvars; v++)
+        CU(cudaMemcpyAsync(&hb[v], &s->scr.req_dst[(int64_t)v * nreq], 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    hb[0] = 0;
+    hb[nvars] = (int64_t)s->h_status[1];
+    if (total_bytes)
+        for (int v = 0; v < nvars; v++) total_bytes[v] = hb[v + 1] - hb[v];
+    int rc = decode_status(s, st, s->h_status[0], bad_index);
+    if (bad_index && *bad_index >= 0) *bad_index %= nreq; // index of the sample in the id list
+    return rc;
+}
+
 // completes a batch issued with DDS_NO_SYNC
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
     if (!s) return fail(DDS_ERR_ARG, "null store");
@@ -898,6 +979,7 @@ int dds_free(dds_store_t *s) {
     s->vars.clear();
     s->zombies.clear();
     s->zombie_blocks.clear();
+    s->multi_key.clear();
     return rc ? rc : rc2;
 }
 
@@ -920,6 +1002,7 @@ void dds_destroy(dds_store_t *s) {
         if (s->d_out) cudaFree(s->d_out);
         if (s->h_status) cudaFreeHost(s->h_status);
         if (s->h_small) cudaFreeHost(s->h_small);
+        if (s->d_multi_vars) cudaFree(s->d_multi_vars);
         if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();

@@ -165,13 +165,20 @@ class RaggedDataset(Dataset):
         One launch chain per variable; the sample-id -> (start, count) lookup happens on the device."""
         ids = np.asarray(indices, dtype=np.int64)
         d_ids = torch.from_numpy(ids).to(self.device, non_blocking=True)
-        out = {}
+        out, bufs, offs, rows = {}, [], [], []
         for name in self.names:
-            rows = int(self.counts[name][ids].sum())  # host-side size of the packed result (sizes only, no data)
-            buf = torch.empty((max(rows, 1),) + tuple(self.widths[name]), dtype=self.dtypes[name], device=self.device)
-            offs = torch.empty(len(ids) + 1, dtype=torch.int64, device=self.device)
-            self.ddstore.get_samples(name, d_ids, out=buf, offsets=offs)
-            out[name] = (buf[:rows], offs // self.row_bytes[name])
+            r = int(self.counts[name][ids].sum())  # host-side size of the packed result (sizes only, no data)
+            rows.append(r)
+            bufs.append(torch.empty((max(r, 1),) + tuple(self.widths[name]), dtype=self.dtypes[name], device=self.device))
+            offs.append(torch.empty(len(ids) + 1, dtype=torch.int64, device=self.device))
+        if len(self.names) <= 4:
+            # every variable of the batch in ONE launch (dds_get_samples_multi)
+            self.ddstore.get_samples_multi(self.names, d_ids, bufs, offsets=offs)
+        else:
+            for name, buf, off in zip(self.names, bufs, offs):
+                self.ddstore.get_samples(name, d_ids, out=buf, offsets=off)
+        for name, buf, off, r in zip(self.names, bufs, offs, rows):
+            out[name] = (buf[:r], off // self.row_bytes[name])
         return out
 
     collate = staticmethod(lambda batch: batch)

@@ -204,6 +204,37 @@ class PyDDStore:
         _capi.raise_for(rc)
         return total.value
 
+    def get_samples_multi(self, names, sample_ids, outs, offsets=None, stream=None, wait=True):
+        """The rows of the same samples in several variables (<= 4, each with a sample index) in ONE launch:
+        outs[v] (CUDA tensors) receive variable names[v]'s packed rows, offsets[v] (optional int64 CUDA tensors of
+        len(ids)+1) the per-sample byte offsets. Returns the list of packed sizes (None when wait=False)."""
+        nv = len(names)
+        obs = [_Buf(o, writable=True) for o in outs]
+        if not all(o.on_device for o in obs):
+            raise ValueError("get_samples_multi delivers into device buffers")
+        s_dev = hasattr(sample_ids, "data_ptr") and getattr(sample_ids, "is_cuda", False)
+        if s_dev:
+            nreq, sp, keep = sample_ids.numel(), sample_ids.data_ptr(), sample_ids
+        else:
+            sa = _i64(sample_ids)
+            nreq, sp, keep = sa.size, sa.ctypes.data, sa
+        flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | _capi.DST_ON_DEVICE | (0 if wait else _capi.NO_SYNC)
+        c_names = (C.c_char_p * nv)(*[n.encode() for n in names])
+        c_dsts = (C.c_void_p * nv)(*[o.ptr for o in obs])
+        c_caps = (C.c_int64 * nv)(*[o.nbytes for o in obs])
+        c_offs = None
+        if offsets is not None:
+            fbs = [_Buf(f, writable=True) for f in offsets]
+            c_offs = (C.c_void_p * nv)(*[f.ptr for f in fbs])
+        totals = (C.c_int64 * nv)()
+        bad = C.c_int64(-1)
+        rc = self._L.dds_get_samples_multi(self._h, nv, c_names, sp, nreq, c_dsts, c_caps, c_offs, flags,
+                                           self._stream_arg(stream), totals, C.byref(bad))
+        del keep
+        self.last_bad_index = bad.value
+        _capi.raise_for(rc)
+        return [totals[v] for v in range(nv)] if wait else None
+
     @staticmethod
     def _stream_arg(stream):
         """None -> the store's own stream; a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)

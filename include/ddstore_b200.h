@@ -151,6 +151,14 @@ int dds_get_samples(dds_store_t *s, const char *name, const int64_t *sample_ids,
                     int64_t dst_capacity, int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
                     int64_t *bad_index);
 
+/* Multi-array samples (BASELINE config 4: node_feat + edge_index per graph): the rows of the SAME nreq samples in
+ * nvars (1..4) variables that each have a sample index, in ONE launch. dsts[v] (device) receives variable v's packed
+ * rows, dst_offsets[v] (nullable, device, nreq+1 entries) its per-sample byte offsets, total_bytes[v] its packed size.
+ * Needs DDS_DST_ON_DEVICE. bad_index is the position in sample_ids of the first failing request. */
+int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, const int64_t *sample_ids, int64_t nreq,
+                          void *const *dsts, const int64_t *dst_capacities, int64_t *const *dst_offsets, unsigned flags,
+                          void *cuda_stream, int64_t *total_bytes, int64_t *bad_index);
+
 /* Completes the batch issued with DDS_NO_SYNC (stream sync + status decode). */
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);
 

@@ -144,6 +144,11 @@ def main():
                 store.get_batch("edge_index", s2, c2, out=o2, stream=side.cuda_stream, wait=False)
 
             timed(both, b1 + b2, f"cfg4 node_feat f32[n,16] + edge_index i64[8n,2], B={B} (2 launches)", {"samples": nsamp})
+            store.set_sample_index("node_feat", dns, dn)
+            store.set_sample_index("edge_index", des, de)
+            timed(lambda: store.get_samples_multi(["node_feat", "edge_index"], ids, [o1, o2], stream=side.cuda_stream,
+                                                  wait=False),
+                  b1 + b2, f"cfg4 both arrays by sample id in ONE launch, B={B}", {"samples": nsamp})
         store.free()
         store = PyDDStore(comm, device=local)
 

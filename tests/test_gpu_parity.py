@@ -553,3 +553,56 @@ def test_overlapped_queue_of_independent_batches(coracle):
         return True
 
     assert all(run_world(1, body))
+
+
+def test_multi_array_batch_in_one_launch(coracle):
+    """dds_get_samples_multi: node_feat + edge_index (+ a third, byte-wide variable) of the same samples in one launch,
+    fused plan (small batch) and separate plan kernels (large batch), against per-variable oracle results."""
+    torch = _torch()
+    rng = np.random.default_rng(17)
+    P, per = 2, 400
+    world = []
+    for r in range(P):
+        n = rng.integers(0, 60, size=per)  # some empty samples
+        feat = rng.integers(0, 2**32, size=(int(n.sum()), 16), dtype=np.uint32).view(np.float32)
+        edge = rng.integers(-2**40, 2**40, size=(int(8 * n.sum()), 2), dtype=np.int64)
+        tags = rng.integers(0, 256, size=(int(3 * n.sum()), 5), dtype=np.uint8)
+        world.append((n, feat, edge, tags))
+    n_all = np.concatenate([w[0] for w in world])
+    tabs = {"node_feat": (n_all, 1), "edge_index": (n_all, 8), "tags": (n_all, 3)}
+    shards = {"node_feat": [w[1] for w in world], "edge_index": [w[2] for w in world], "tags": [w[3] for w in world]}
+
+    def body(store, r):
+        names = ["node_feat", "edge_index", "tags"]
+        for nm in names:
+            store.add(nm, shards[nm][r])
+            cnt = tabs[nm][0] * tabs[nm][1]
+            store.set_sample_index(nm, np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt)
+        for B in (37, 5000):
+            ids = rng.integers(0, P * per, size=B)
+            exp = {}
+            for nm in names:
+                cnt = tabs[nm][0] * tabs[nm][1]
+                st = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+                exp[nm] = coracle.get_batch(shards[nm], st[ids], cnt[ids])
+            outs = [torch.zeros(max(exp[nm][0].size, 16) + 32, dtype=torch.uint8, device="cuda:0") for nm in names]
+            offs = [torch.zeros(B + 1, dtype=torch.int64, device="cuda:0") for _ in names]
+            totals = store.get_samples_multi(names, ids, outs, offsets=offs)
+            for nm, o, f, t in zip(names, outs, offs, totals):
+                e, eo, bad, _ = exp[nm]
+                assert bad == -1 and t == e.size, (nm, t, e.size)
+                assert o[:t].cpu().numpy().tobytes() == e.tobytes(), nm
+                assert int(o[t:].sum()) == 0 and f.cpu().tolist() == eo.tolist()
+        # an out-of-range sample id is reported with its position in the id list
+        ids = np.array([1, 2, P * per + 3, 4])
+        with pytest.raises(ValueError, match="sample id"):
+            store.get_samples_multi(names, ids, outs)
+        assert store.last_bad_index == 2
+        # capacity of ONE variable too small
+        ids = rng.integers(0, P * per, size=64)
+        small = [outs[0], outs[1][:8], outs[2]]
+        with pytest.raises(ValueError, match="too small"):
+            store.get_samples_multi(names, ids, small)
+        return True
+
+    assert all(run_world(P, body))
