@@ -10,11 +10,20 @@ if ROOT not in sys.path:
 
 
 def _ensure_built():
-    """the native pieces are built in-tree by __graft_entry__.build(); if this checkout has not been built yet
-    (fresh clone: *.so is git-ignored), build now rather than fail every test at import"""
+    """the native pieces are built in-tree by __graft_entry__.build(); build now if this checkout has not been built
+    yet (fresh clone: *.so is git-ignored) or if a source is newer than the library it goes into"""
+    import glob
     lib = os.path.join(ROOT, "ddstore_b200", "libddstore_b200.so")
-    cy = [f for f in os.listdir(os.path.join(ROOT, "ddstore_b200", "cython")) if f.startswith("pyddstore") and f.endswith(".so")]
-    if not os.path.exists(lib) or not cy or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+    cy = glob.glob(os.path.join(ROOT, "ddstore_b200", "cython", "pyddstore*.so"))
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    stale = not os.path.exists(lib) or not cy or not os.path.exists(orc)
+    if not stale:
+        srcs = glob.glob(os.path.join(ROOT, "ddstore_b200", "csrc", "*.c*")) + \
+            glob.glob(os.path.join(ROOT, "ddstore_b200", "csrc", "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h*"))
+        stale = max(os.path.getmtime(f) for f in srcs) > os.path.getmtime(lib) or \
+            os.path.getmtime(os.path.join(ROOT, "ddstore_b200", "cython", "pyddstore.pyx")) > os.path.getmtime(cy[0]) or \
+            os.path.getmtime(os.path.join(ROOT, "oracle", "ddstore_oracle.c")) > os.path.getmtime(orc)
+    if stale:
         import __graft_entry__
         __graft_entry__.build()
 
