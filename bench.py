@@ -350,7 +350,9 @@ def run_ours(args):
     store.wait()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    per_launch_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    pair_list = [a.elapsed_time(b) for a, b in ev]
+    per_launch_ms = float(np.mean(pair_list))
+    pair_pcts = [float(np.percentile(pair_list, q)) for q in (10, 50, 90)]
     if N > 1:
         t = torch.tensor([ms_total, per_launch_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,7 +412,7 @@ def run_ours(args):
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]  # per launch, from the committed ncu --set full capture
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "dds_gather_kernel<FIXED>", "per_launch_ms": per_launch_ms,
-                "per_launch_event_pair_ms": pair_ms,
+                "per_launch_event_pair_ms": pair_ms, "per_launch_event_pair_ms_p10_p50_p90": pair_pcts,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "note": note}
 
     if rank == 0:
