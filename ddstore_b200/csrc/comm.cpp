@@ -179,6 +179,7 @@ dds_comm_t *dds_comm_shm(const char *key, int rank, int size) {
     }
     // everyone has the segment mapped after this barrier; the name can go away so no stale file survives
     if (shm_barrier(c) != DDS_OK) {
+        if (creator) shm_unlink(name.c_str()); // a failed rendezvous must not leave a half-used segment behind
         munmap(m, bytes);
         delete c;
         return nullptr;

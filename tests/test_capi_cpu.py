@@ -218,3 +218,59 @@ def test_data_plane_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError, match="No usable CUDA device"):
         PyDDStore()
     assert _capi.lib().dds_create(None, 0, 0) is None
+
+
+def test_shm_comm_times_out_instead_of_hanging(monkeypatch):
+    """a rank that never arrives must produce an error, not a hang (the reference hangs in MPI_Get / MPI_Win_fence)"""
+    import time
+    monkeypatch.setenv("DDS_COMM_TIMEOUT_S", "1")
+    from ddstore_b200.comm import ShmComm
+    key = "to" + uuid.uuid4().hex[:10]
+    t0 = time.time()
+    with pytest.raises(RuntimeError, match="barrier timed out|timed out"):
+        ShmComm(key, 0, 2)  # rank 1 never shows up
+    assert time.time() - t0 < 30
+    # the creator could not unlink the name (the rendezvous never completed): a later job with the SAME key is told so
+    with pytest.raises(RuntimeError, match="stale or mismatched|timed out"):
+        ShmComm(key, 0, 2)
+    try:
+        os.unlink("/dev/shm/dds_b200_" + key)
+    except OSError:
+        pass
+
+
+def test_callback_comm_errors_propagate():
+    from ddstore_b200.comm import CallbackComm
+
+    def bad_allgather(b):
+        raise ValueError("boom")
+
+    c = CallbackComm(0, 2, bad_allgather, lambda: None)
+    out = np.zeros(2, np.int64)
+    rc = _capi.lib().dds_exchange_lenlist(c.handle, 5, 1, out.ctypes.data_as(_capi.I64P))
+    assert rc == _capi.ERR_COMM and "allgather callback failed" in _capi.last_error()
+    c.close()
+
+
+def test_as_dds_comm_accepts_mpi4py_like_objects():
+    from ddstore_b200.comm import as_dds_comm
+
+    class FakeMPIComm:  # the four methods of mpi4py.MPI.Comm the adapter uses
+        def Get_rank(self):
+            return 0
+
+        def Get_size(self):
+            return 1
+
+        def allgather(self, b):
+            return [b]
+
+        def Barrier(self):
+            pass
+
+    c = as_dds_comm(FakeMPIComm())
+    assert c.Get_rank() == 0 and c.Get_size() == 1 and c.allgather_bytes(b"xy") == [b"xy"]
+    c.Barrier()
+    c.close()
+    with pytest.raises(TypeError):
+        as_dds_comm(object())
