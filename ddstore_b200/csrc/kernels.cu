@@ -267,9 +267,12 @@ struct GatherArgs {
     char *mdst[DDSK_MAX_MULTI];
     int64_t mcap[DDSK_MAX_MULTI];
     int64_t *moffsets[DDSK_MAX_MULTI]; // optional per-variable [per_var + 1] byte offsets
-    int overlap;   // FIXED, declared independent of its neighbours in the queue: touch no shared mutable state
-                   // (segments are strided statically instead of ticketed)
+    int overlap;   // declared independent of its neighbours in the queue: segments are strided statically instead of
+                   // ticketed; a variable-count launch then works in its own scratch slot with monotonic counters
     int skip_wait; // ... and the launch before it was one too: do not wait for it to finish
+    unsigned int ticket_base, tiles_base, finish_target; // VAR + overlap: values of the slot's monotonic counters
+                                                         // [2] (plan tickets), [3] (tiles done), [1] (warps finished)
+                                                         // after every earlier user of the slot
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
 };
 
@@ -517,9 +520,9 @@ __device__ __forceinline__ void plan_in_kernel(const GatherArgs &a, int lane) {
     const int64_t ntiles = (a.nreq + TILE_REQ - 1) / TILE_REQ;
     while (true) {
         unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(&a.counters[2], 1u);
+        if (lane == 0) tile = atomicAdd(&a.counters[2], 1u) - a.ticket_base; // base = 0 for self-resetting counters
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if ((int64_t)tile >= ntiles) break;
+        if ((int64_t)tile >= ntiles) break; // (every warp makes exactly one failing claim: the host counts on that)
         // lane owns TILE_ITEMS consecutive requests
         int64_t idx[TILE_ITEMS], nb[TILE_ITEMS];
         uint64_t sv[TILE_ITEMS];
@@ -585,7 +588,7 @@ __device__ __forceinline__ void plan_in_kernel(const GatherArgs &a, int lane) {
     // every tile has an owner that is running; wait until all of them have written their part of the plan
     if (lane == 0) {
         const uint64_t t0 = globaltimer_ns();
-        while ((int64_t)ld_acquire_u32(&a.counters[3]) < ntiles) {
+        while ((int64_t)(unsigned int)(ld_acquire_u32(&a.counters[3]) - a.tiles_base) < ntiles) {
             __nanosleep(200);
             if (globaltimer_ns() - t0 > 4000000000ull) {
                 report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
@@ -625,7 +628,21 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     // head of batch k+1 overlap, whatever else is running on the GPU.
     // (The first batch of such a run still waits, so a ticketed launch before the run has retired for good before
     // any ticketed launch after the run can start.)
-    if (!(FIXED && a.skip_wait)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!a.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!FIXED && a.overlap) {
+        // the scratch slot of an overlapped variable-count batch is reused every few launches: its previous user must
+        // have retired completely (all of ITS CTAs have started long ago, so this cannot deadlock)
+        if (lane == 0) {
+            const uint64_t t0 = globaltimer_ns();
+            while ((int)(ld_acquire_u32(&a.counters[1]) - a.finish_target) < 0) {
+                __nanosleep(100);
+                if (globaltimer_ns() - t0 > 4000000000ull) {
+                    report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                    __trap();
+                }
+            }
+        }
+    }
     __syncwarp();
 
     if (!FIXED && a.fused_plan) plan_in_kernel(a, lane);
@@ -634,7 +651,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     ChunkWalker<FIXED, CH> w;
     w.gwarp = gwarp;
     w.nwarps = nwarps;
-    w.static_claims = FIXED && a.overlap;
+    w.static_claims = a.overlap != 0;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
     bool over = w.T > a.dst_cap;
@@ -778,8 +795,12 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
     }
 
+    if (!FIXED && a.overlap && lane == 0) { // this warp is done with the slot's plan arrays
+        __threadfence();
+        atomicAdd(&a.counters[1], 1u);
+    }
     // ---- self-resetting ticket counters (not used by overlapped launches) ---------------------
-    if (lane == 0 && !(FIXED && a.overlap)) {
+    if (lane == 0 && !a.overlap) {
         __threadfence();
         unsigned int done = atomicAdd(&a.counters[1], 1u);
         if (done == (unsigned int)(nwarps - 1)) {
@@ -1120,7 +1141,8 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
     p.nsamples = index->nsamples;
     // measured (profiles/r1_configs.md): the in-kernel plan wins below ~8K requests (one launch instead of two or
     // three: B=4096 54 -> 48 us), separate plan kernels are ~2 % faster above (they overlap the previous gather's tail)
-    const bool fused = g_fused_plan == 1 ? nreq <= 8192 : g_fused_plan == 2;
+    const bool ovl = (reset_status & 4) != 0; // independent batch in its own scratch slot: always planned in-kernel
+    const bool fused = ovl || (g_fused_plan == 1 ? nreq <= 8192 : g_fused_plan == 2);
     if (!fused) {
         // one CTA is enough for explicit (start, count) arrays (coalesced loads); the sample-index lookups are random
         // two-level gathers and want more SMs' worth of memory parallelism (measured: 1 CTA costs +25 us at B=4096)
@@ -1160,6 +1182,21 @@ int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nr
         a.epoch = scr->epoch;
         a.fused_plan = 1;
         a.offsets_out = offsets_dev_or_null;
+    }
+    if (ovl) {
+        a.overlap = 1;
+        a.skip_wait = (reset_status & 16) ? 1 : 0;
+        a.ticket_base = scr->ticket_base;
+        a.tiles_base = scr->tiles_base;
+        a.finish_target = scr->finish_target;
+        const Geometry &g = kGeoms[geometry_for(false, 0)];
+        int per_sm = g_ctas_per_sm;
+        while (per_sm > 1 && per_sm * (g.nw * g.stages * (g.ch + 32) + 2048) > 227 * 1024) per_sm--;
+        const unsigned int nwarps = (unsigned int)(g_sms * per_sm * g.nw);
+        const unsigned int ntiles = (unsigned int)((nreq + TILE_REQ - 1) / TILE_REQ);
+        scr->ticket_base += ntiles + nwarps; // every warp makes exactly one failing ticket claim
+        scr->tiles_base += ntiles;
+        scr->finish_target += nwarps;
     }
     return launch_gather<false>(a, st);
 }

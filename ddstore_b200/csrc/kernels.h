@@ -44,12 +44,16 @@ typedef struct ddsk_scratch {
     unsigned long long *host_mirror; /* device alias of 2 pinned host words: status, packed total (written by the
                                         last warp of every gather launch); NULL = not used */
     unsigned int epoch;         /* host-side launch counter tagging the look-back words (22 bits, 0 = never) */
+    /* slots used by overlapped variable-count launches: their counters only ever grow; these are the values they
+     * will have once every launch queued on the slot so far has retired */
+    unsigned int ticket_base, tiles_base, finish_target;
 } ddsk_scratch_t;
 
 /* `flags` of both launchers: bit 0 = reset the status word first, bit 1 = have the kernel's last warp mirror status +
  * total into scr->host_mirror (synchronous calls; costs ~2 us at the kernel's end, so async queues skip it);
- * fixed entry only: bit 2 = independent batch (static segment striding instead of the ticket counters: no shared
- * mutable state), bit 4 = its predecessor in the queue was one too (skip griddepcontrol.wait: the two overlap).
+ * bit 2 = independent batch (static segment striding instead of the ticket counters; for the variable entry `scr` must
+ * then be a scratch slot of its own, used with monotonic counters and planned in-kernel), bit 4 = its predecessor in
+ * the queue was one too (skip griddepcontrol.wait: the two overlap).
  * Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
  * One launch: validate + owner lookup + gather + pack. */
 int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,

@@ -149,6 +149,11 @@ struct dds_store {
     cudaStream_t pending_stream = nullptr;
     int64_t pending_fixed_total = -1;
     int64_t pending_nreq = 0;
+    // scratch slots of overlapped variable-count batches (DDS_OVERLAP): each launch plans into its own slot
+    static constexpr int kRing = 4;
+    ddsk_scratch_t ring[kRing];
+    int ring_next = 0;
+    const int64_t *pending_total_ptr = nullptr; // device word holding the packed total of the last queued launch
     ddsk_var_t *d_multi_vars = nullptr; // device copy of the windows of the last multi-array combination
     std::string multi_key;
     bool prev_fixed = false;
@@ -181,6 +186,32 @@ int ensure_scratch(dds_store *s, int64_t nreq) {
     CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 128 + 2) * 8));
     CU(cudaMemset(s->scr.tile_sums, 0, (size_t)(cap / 128 + 2) * 8));
     s->scr.cap_req = cap;
+    return DDS_OK;
+}
+
+int ensure_ring(dds_store *s, int64_t nreq, cudaStream_t st) {
+    if (s->ring[0].cap_req >= nreq) return DDS_OK;
+    int64_t cap = std::max<int64_t>(8192, s->ring[0].cap_req);
+    while (cap < nreq) cap *= 2;
+    CU(cudaStreamSynchronize(st)); // nothing queued may still be using the old slots
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < dds_store::kRing; k++) {
+        ddsk_scratch_t &r = s->ring[k];
+        if (r.req_src) cudaFree(r.req_src);
+        if (r.req_dst) cudaFree(r.req_dst);
+        if (r.tile_sums) cudaFree(r.tile_sums);
+        if (r.counters) cudaFree(r.counters);
+        memset(&r, 0, sizeof(r));
+        CU(cudaMalloc((void **)&r.req_src, (size_t)cap * 8));
+        CU(cudaMalloc((void **)&r.req_dst, (size_t)(cap + 1) * 8));
+        CU(cudaMalloc((void **)&r.tile_sums, (size_t)(cap / 128 + 2) * 8));
+        CU(cudaMemset(r.tile_sums, 0, (size_t)(cap / 128 + 2) * 8));
+        CU(cudaMalloc((void **)&r.counters, 16));
+        CU(cudaMemset(r.counters, 0, 16));
+        r.status = s->scr.status; // one sticky status word per store
+        r.host_mirror = nullptr;
+        r.cap_req = cap;
+    }
     return DDS_OK;
 }
 
@@ -519,6 +550,7 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
     }
     dds_store *s = new dds_store;
     memset(&s->scr, 0, sizeof(s->scr));
+    memset(s->ring, 0, sizeof(s->ring));
     s->comm = comm;
     s->rank = dds_comm_rank(comm);
     s->size = dds_comm_size(comm);
@@ -712,8 +744,19 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             ix.starts = d_starts;
             ix.counts = d_counts;
         }
-        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &s->scr, no_sync ? 0 : 2, st);
-        s->prev_overlap = false;
+        // DDS_OVERLAP on a variable-count batch: plan + gather in a scratch slot of its own (ring of kRing)
+        const bool ovl = no_sync && (flags & DDS_OVERLAP);
+        ddsk_scratch_t *scr = &s->scr;
+        if (ovl) {
+            if (int rc = ensure_ring(s, nreq, st)) return rc;
+            scr = &s->ring[s->ring_next];
+            s->ring_next = (s->ring_next + 1) % dds_store::kRing;
+        }
+        const bool skip = ovl && chain && s->prev_overlap;
+        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, scr, (no_sync ? 0 : 2) | (ovl ? 4 : 0) | (skip ? 16 : 0),
+                              st);
+        s->prev_overlap = ovl;
+        s->pending_total_ptr = &scr->req_dst[nreq];
     }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
@@ -867,6 +910,7 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
     s->prev_fixed = false;
     s->pending_fixed_total = -1;
     s->pending_nreq = nreq * nvars;
+    s->pending_total_ptr = &s->scr.req_dst[nreq * nvars];
     if (no_sync) {
         s->pending = true;
         s->pending_stream = st;
@@ -896,7 +940,8 @@ int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
     // queued launches skip the host mirror (it costs ~2 us at the end of every kernel): read the words back here
     CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
     if (s->pending_fixed_total < 0)
-        CU(cudaMemcpyAsync(&s->h_status[1], &s->scr.req_dst[s->pending_nreq], 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&s->h_status[1], s->pending_total_ptr ? s->pending_total_ptr : &s->scr.req_dst[s->pending_nreq], 8,
+                           cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = s->pending_fixed_total >= 0 ? s->pending_fixed_total : (int64_t)s->h_status[1];
     return decode_status(s, st, s->h_status[0], bad_index);
@@ -1005,6 +1050,12 @@ void dds_destroy(dds_store_t *s) {
         if (s->h_status) cudaFreeHost(s->h_status);
         if (s->h_small) cudaFreeHost(s->h_small);
         if (s->d_multi_vars) cudaFree(s->d_multi_vars);
+        for (int k = 0; k < dds_store::kRing; k++) {
+            if (s->ring[k].req_src) cudaFree(s->ring[k].req_src);
+            if (s->ring[k].req_dst) cudaFree(s->ring[k].req_dst);
+            if (s->ring[k].tile_sums) cudaFree(s->ring[k].tile_sums);
+            if (s->ring[k].counters) cudaFree(s->ring[k].counters);
+        }
         if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();

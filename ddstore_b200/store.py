@@ -120,8 +120,8 @@ class PyDDStore:
         (same residency as `out`). Returns the number of packed bytes.
         wait=False (device indices + device out only): enqueue on `stream` and return at once; call
         `wait()` later for the status. Several such batches may be queued on one stream.
-        overlap=True (with wait=False, fixed count): this batch is independent of the one queued just before it
-        (different `out`, indices not written by it) and may overlap with its tail -- double-buffered prefetch.
+        overlap=True (with wait=False): this batch is independent of the one queued just before it (different `out`
+        and `offsets`, indices not written by it) and may overlap with its tail -- double-buffered prefetch.
         Raises the reference's ValueError for the first invalid request (requests before it are delivered).
         """
         itemsize = self._itemsize.get(name)
@@ -174,7 +174,7 @@ class PyDDStore:
         _capi.raise_for(self._L.dds_set_sample_index(self._h, name.encode(), sp, cp, n, 1 if dev else 0))
         del keep
 
-    def get_samples(self, name, sample_ids, out, offsets=None, stream=None, wait=True):
+    def get_samples(self, name, sample_ids, out, offsets=None, stream=None, wait=True, overlap=False):
         """get_batch by SAMPLE ID: the id -> (start, count) lookup runs inside the launch, against the index
         registered with set_sample_index. Same packing / offsets / error behaviour as get_batch."""
         itemsize = self._itemsize.get(name)
@@ -189,7 +189,7 @@ class PyDDStore:
             nreq, sp, keep = sa.size, sa.ctypes.data, sa
         flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | (_capi.DST_ON_DEVICE if ob.on_device else 0)
         if not wait:
-            flags |= _capi.NO_SYNC
+            flags |= _capi.NO_SYNC | (_capi.OVERLAP if overlap else 0)
         op = None
         if offsets is not None:
             fb = _Buf(offsets, writable=True)

@@ -131,10 +131,11 @@ int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int 
 #define DDS_IDX_ON_DEVICE 1u /* starts / counts are device pointers */
 #define DDS_DST_ON_DEVICE 2u /* dst / dst_offsets are device pointers */
 #define DDS_NO_SYNC 4u       /* needs both flags above: enqueue on cuda_stream and return; dds_batch_wait() reports */
-#define DDS_OVERLAP 8u       /* with DDS_NO_SYNC, fixed-count batches: this batch is INDEPENDENT of the batch queued just
-                              * before it on the same stream (different destination buffer; indices not produced by
-                              * it), so the two may overlap: the head of this one fills the SMs the tail of the
-                              * previous one vacates (double-buffered prefetch). Ignored when it does not apply. */
+#define DDS_OVERLAP 8u       /* with DDS_NO_SYNC: this batch is INDEPENDENT of the batch queued just before it on the same
+                              * stream (different destination / offsets buffers; indices not produced by it), so the
+                              * two may overlap: the head of this one fills the SMs the tail of the previous one vacates
+                              * (double-buffered prefetch). Variable-count batches then plan in a scratch slot of
+                              * their own. Ignored when it does not apply. */
 int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const int64_t *counts,
                   int64_t fixed_count, int64_t nreq, int itemsize, void *dst, int64_t dst_capacity,
                   int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,

@@ -115,6 +115,15 @@ def main():
                 store.set_sample_index("x", d_start, d_len)
             timed(lambda: store.get_samples("x", ids, out, offsets=offs, stream=side.cuda_stream, wait=False), nbytes,
                   f"cfg3 by sample id (device index), B={B}", {"samples": nsamp})
+            out_b, offs_b = torch.empty_like(out), torch.empty_like(offs)
+            flip = [0]
+
+            def queued():
+                flip[0] ^= 1
+                store.get_samples("x", ids, out_b if flip[0] else out, offsets=offs_b if flip[0] else offs,
+                                  stream=side.cuda_stream, wait=False, overlap=True)
+
+            timed(queued, nbytes, f"cfg3 by sample id, DDS_OVERLAP double-buffered queue, B={B}", {"samples": nsamp})
         store.free()
         store = PyDDStore(comm, device=local)
 

@@ -606,3 +606,47 @@ def test_multi_array_batch_in_one_launch(coracle):
         return True
 
     assert all(run_world(P, body))
+
+
+def test_overlapped_queue_of_variable_count_batches(coracle):
+    """DDS_OVERLAP on variable-count batches: every launch plans in its own scratch slot (ring of 4, monotonic counters,
+    slot-reuse guard); explicit and by-sample requests, small and large batches, 11 launches deep."""
+    torch = _torch()
+    rng = np.random.default_rng(55)
+    nsamp = 30_000
+    L = rng.integers(0, 200, size=nsamp)
+    sstart = np.concatenate([[0], np.cumsum(L)])
+    shard = rng.integers(0, 2**32, size=(int(sstart[-1]), 3), dtype=np.uint32).view(np.float32)  # 12 B rows: re-phase path
+
+    def body(store, r):
+        store.add("x", shard)
+        store.set_sample_index("x", sstart[:-1], L)
+        dev = torch.device("cuda", 0)
+        side = torch.cuda.Stream(device=dev)
+        sizes = [300, 9000, 5000, 20000, 700, 9000, 9000, 300, 20000, 5000, 1234]
+        batches = [rng.integers(0, nsamp, size=B) for B in sizes]
+        exps = [coracle.get_batch([shard], sstart[b], L[b]) for b in batches]
+        cap = max(e[0].size for e in exps) + 64
+        bufs = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        offs = [torch.zeros(max(sizes) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        d_ids = [torch.from_numpy(b).to(dev) for b in batches]
+        d_st = [torch.from_numpy(sstart[b]).to(dev) for b in batches]
+        d_ct = [torch.from_numpy(L[b]).to(dev) for b in batches]
+        torch.cuda.synchronize()
+        for k in range(len(batches)):
+            o, f = bufs[k & 1], offs[k & 1][:sizes[k] + 1]
+            if k % 3 == 0:
+                store.get_samples("x", d_ids[k], o, offsets=f, stream=side.cuda_stream, wait=False, overlap=True)
+            elif k == 4:  # an ordinary queued launch in the middle of the run
+                store.get_batch("x", d_st[k], d_ct[k], out=o, offsets=f, stream=side.cuda_stream, wait=False)
+            else:
+                store.get_batch("x", d_st[k], d_ct[k], out=o, offsets=f, stream=side.cuda_stream, wait=False, overlap=True)
+        total = store.wait()
+        assert total == exps[-1][0].size
+        for slot, k in ((0, 10), (1, 9)):
+            e, eo, bad, _ = exps[k]
+            assert bad == -1 and bufs[slot][:e.size].cpu().numpy().tobytes() == e.tobytes(), f"buffer {slot} != batch {k}"
+            assert offs[slot][:sizes[k] + 1].cpu().tolist() == eo.tolist()
+        return True
+
+    assert all(run_world(1, body))
