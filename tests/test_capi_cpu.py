@@ -274,3 +274,36 @@ def test_as_dds_comm_accepts_mpi4py_like_objects():
     c.close()
     with pytest.raises(TypeError):
         as_dds_comm(object())
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C-ABI: include/ddstore_b200.h must compile as C99, not just as C++"""
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "ddstore_b200.h"\nint main(void) { dds_varinfo_t v; (void)v; return DDS_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_locate_property_against_oracle_and_reference(coracle):
+    """hypothesis: for arbitrary (also degenerate) lenlists and requests, the C-ABI's host lookup, the C oracle and --
+    when it is built -- the compiled reference agree on owner, offset and error class"""
+    from hypothesis import given, settings, strategies as st
+    from oracle import oracle as O
+    ref = O.RefWorld(1) if O.have_ref() else None
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(0, 40), min_size=1, max_size=12), st.integers(-5, 500), st.integers(0, 60))
+    def check(nrows, start, count):
+        ll = np.cumsum(np.array(nrows, np.int64))
+        t, off, rc = coracle.locate(ll, start, count)
+        assert _locate(ll, start, count) == (t, off, rc)
+        assert _ss(ll, start) == coracle.sortedsearch(ll, start)
+        if ref is not None:
+            assert ref.sortedsearch(ll, start) == coracle.sortedsearch(ll, start)
+
+    try:
+        check()
+    finally:
+        if ref is not None:
+            ref.close()
