@@ -25,5 +25,29 @@ for dtype, disp in ((np.uint8, 7), (np.float32, 1), (np.float32, 1024), (np.int6
         o2 = torch.zeros(max(e2.size, 16), dtype=torch.uint8, device="cuda")
         store.get_batch(name, torch.tensor(ok).cuda(), out=o2, count=2)
         assert o2[:e2.size].cpu().numpy().tobytes() == e2.tobytes()
+# sample index, multi-array launch, overlapped queues (fixed and variable counts)
+L = rng.integers(0, 30, size=400)
+ss = np.concatenate([[0], np.cumsum(L)])
+feat = rng.integers(0, 2**32, size=(int(ss[-1]), 4), dtype=np.uint32).view(np.float32)
+edge = rng.integers(-9, 9, size=(int(2 * ss[-1]), 2), dtype=np.int64)
+store.add("feat", feat); store.add("edge", edge)
+store.set_sample_index("feat", ss[:-1], L); store.set_sample_index("edge", 2 * ss[:-1], 2 * L)
+ids = rng.integers(0, 400, size=333)
+ef = co.get_batch([feat], ss[ids], L[ids])[0]; ee = co.get_batch([edge], 2 * ss[ids], 2 * L[ids])[0]
+of = torch.zeros(ef.size + 16, dtype=torch.uint8, device="cuda"); oe = torch.zeros(ee.size + 16, dtype=torch.uint8, device="cuda")
+tot = store.get_samples_multi(["feat", "edge"], ids, [of, oe])
+assert tot == [ef.size, ee.size] and of[:ef.size].cpu().numpy().tobytes() == ef.tobytes() and oe[:ee.size].cpu().numpy().tobytes() == ee.tobytes()
+side = torch.cuda.Stream()
+d_ids = torch.from_numpy(ids).cuda()
+bufs = [torch.zeros_like(of), torch.zeros_like(of)]
+torch.cuda.synchronize()
+for k in range(6):
+    store.get_samples("feat", d_ids, bufs[k & 1], stream=side.cuda_stream, wait=False, overlap=True)
+assert store.wait() == ef.size and bufs[1][:ef.size].cpu().numpy().tobytes() == ef.tobytes()
+fx = torch.from_numpy(rng.integers(0, 2990, size=500)).cuda()
+ofx = [torch.zeros(500 * 2 * 28, dtype=torch.uint8, device="cuda") for _ in range(2)]
+for k in range(6):
+    store.get_batch("v7_uint8", fx, out=ofx[k & 1][:500 * 2 * 7], count=2, stream=side.cuda_stream, wait=False, overlap=True)
+store.wait()
 store.free(); store.close()
 print("sanitize-ok")
