@@ -386,8 +386,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel
     peaks, peak_src = measured_peaks()
-    geom = [__import__("ctypes").c_int() for _ in range(5)]
-    _capi.lib().dds_gather_geometry(*[__import__("ctypes").byref(g) for g in geom])
+    import ctypes
+    geom = [ctypes.c_int() for _ in range(5)]
+    _capi.lib().dds_gather_geometry(*[ctypes.byref(g) for g in geom])
     if N == 1:
         bound, alg_bytes, peak = "hbm", 2 * step_bytes, float(peaks["hbm_gbs"])
         note = ("algorithmic bytes per launch = 2 x payload (each byte read once from HBM, written once to HBM); "

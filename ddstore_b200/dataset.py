@@ -128,7 +128,7 @@ class RaggedDataset(Dataset):
         self.ddstore = PyDDStore(self.comm, device=self.device.index)
         self.names = list(local_arrays)
         self.row_bytes, self.dtypes, self.widths = {}, {}, {}
-        self.starts, self.counts = {}, {}
+        self.counts = {}  # host copy of every sample's row count per variable (sizes the packed outputs)
         n_local = len(next(iter(local_counts.values())))
         for name in self.names:
             arr = np.ascontiguousarray(local_arrays[name])

@@ -21,7 +21,7 @@ _TORCH_OK = {"torch.int32", "torch.int64", "torch.uint8", "torch.float32", "torc
 class _Buf:
     """pointer / shape / itemsize / residency of an ndarray, a CUDA tensor or a CAI object"""
 
-    def __init__(self, arr, writable=False):
+    def __init__(self, arr, writable=False):  # `writable` documents intent at the call sites; nothing is copied
         self.keep = arr
         if isinstance(arr, np.ndarray):
             assert arr.flags.c_contiguous  # src/pyddstore.pyx:66,85,116
