@@ -26,11 +26,15 @@
 //       - different phase -> all lanes read two aligned 16-byte vectors from shared memory,
 //         funnel-shift (or word-select) them into place and issue aligned 128-bit stores.
 //   * Request offsets in the packed buffer are an exclusive prefix sum of request sizes: arithmetic
-//     in the fixed-count entry; for variable counts a warp-shuffle scan with decoupled look-back
-//     INSIDE the gather launch (<= 8192 requests) or in two small plan kernels before it. The
-//     (start, count) of a request may come from a device-resident per-sample index (sample ids in).
+//     in the fixed-count entry. For variable counts and <= 8192 requests EVERY CTA computes the whole
+//     plan (lookup + checks + scan) redundantly into its own shared memory -- no inter-CTA
+//     dependency at all, and the walk's searches / descriptor loads are shared-memory reads.
+//     Larger batches are planned by two small kernels into global scratch, which also fill a
+//     segment table (request covering every 16 KiB boundary) so a segment claim is one load.
+//     The (start, count) of a request may come from a device-resident per-sample index (sample ids in).
 //   * Launches carry the programmatic-dependent-launch attribute; independent batches
-//     (DDS_OVERLAP) skip the grid wait and overlap head-to-tail.
+//     (DDS_OVERLAP) skip the grid wait and overlap head-to-tail, under a contract the kernel
+//     enforces itself with per-launch generation words (see the overlap protocol below).
 //
 // Nothing here calls a library kernel; everything is launched from the ddsk_* functions at the end.
 #include <cuda_runtime.h>
@@ -149,29 +153,59 @@ __device__ __forceinline__ void report(unsigned long long *status, int64_t req, 
     atomicMin(status, ((unsigned long long)req << 8) | (unsigned long long)code);
 }
 
+// a few more PTX helpers used below
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { // full completion (global writes performed), not just the smem reads
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // gather kernel
 // ------------------------------------------------------------------------------------------------
 // where request i's (start row, row count) comes from: explicit arrays, or a per-sample table indexed by ids[i]
 struct PlanSrc {
-    const int64_t *starts, *counts;       // explicit (ids == nullptr)
-    const int64_t *ids;                   // sample ids (device-resident sample index)
-    const int64_t *tab_start, *tab_count; // [nsamples] row_start / row_count of every sample of this variable
+    const int64_t *starts, *counts; // explicit (ids == nullptr)
+    const int64_t *ids;             // sample ids (device-resident sample index)
+    const longlong2 *tab;           // [nsamples] {row_start, row_count} of every sample of this variable: ONE 16-byte load
     int64_t nsamples;
     // multi-array batches (config 4: node_feat + edge_index of the same samples in ONE launch): request i belongs to
     // variable i / per_var and to sample ids[i % per_var]; every variable has its own window and sample index
-    int nvars;                                   // 0/1: single variable
-    int64_t per_var;                             // requests per variable (= number of sample ids)
-    const ddsk_var_t *mvars;                     // [nvars] windows, device memory
-    const int64_t *mtab_start[DDSK_MAX_MULTI], *mtab_count[DDSK_MAX_MULTI];
+    int nvars;               // 0/1: single variable
+    int64_t per_var;         // requests per variable (= number of sample ids)
+    const ddsk_var_t *mvars; // [nvars] windows, device memory
+    const longlong2 *mtab[DDSK_MAX_MULTI];
     int64_t mnsamples[DDSK_MAX_MULTI];
 };
 
-// Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as three unrolled passes
+__device__ __forceinline__ longlong2 ldg_pair(const longlong2 *p) { return __ldg(p); }
+
+// Lookup + checks of K requests per thread -> (source address or 0, byte size). Written as unrolled passes
 // (ids, then table rows, then arithmetic) so that the K independent -- and for the sample index, dependent
 // two-level -- global loads of a thread are all in flight together instead of one DRAM latency after another.
+// `limit`: requests idx >= limit are not this thread's business (dead lanes).
 template <int K>
-__device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &p, const int64_t (&idx)[K], int64_t nreq,
+__device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &p, const int64_t (&idx)[K], int64_t limit,
                                           unsigned long long *status, uint64_t (&src)[K], int64_t (&nbytes)[K]) {
     int64_t start[K], count[K];
     bool live[K], badid[K];
@@ -181,7 +215,7 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
         int v[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            live[k] = idx[k] < nreq;
+            live[k] = idx[k] < limit;
             v[k] = live[k] ? (int)(idx[k] / p.per_var) : 0;
             id[k] = live[k] ? p.ids[idx[k] - (int64_t)v[k] * p.per_var] : 0;
             vp[k] = &p.mvars[v[k]];
@@ -190,14 +224,15 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
         for (int k = 0; k < K; k++) {
             badid[k] = live[k] && (id[k] < 0 || id[k] >= p.mnsamples[v[k]]);
             const bool ok = live[k] && !badid[k];
-            start[k] = ok ? p.mtab_start[v[k]][id[k]] : 0;
-            count[k] = ok ? p.mtab_count[v[k]][id[k]] : 0;
+            const longlong2 e = ok ? ldg_pair(&p.mtab[v[k]][id[k]]) : make_longlong2(0, 0);
+            start[k] = e.x;
+            count[k] = e.y;
         }
     } else if (p.ids) {
         int64_t id[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            live[k] = idx[k] < nreq;
+            live[k] = idx[k] < limit;
             id[k] = live[k] ? p.ids[idx[k]] : 0;
             vp[k] = &var;
         }
@@ -205,13 +240,14 @@ __device__ __forceinline__ void plan_many(const ddsk_var_t &var, const PlanSrc &
         for (int k = 0; k < K; k++) {
             badid[k] = live[k] && (id[k] < 0 || id[k] >= p.nsamples);
             const bool ok = live[k] && !badid[k];
-            start[k] = ok ? p.tab_start[id[k]] : 0;
-            count[k] = ok ? p.tab_count[id[k]] : 0;
+            const longlong2 e = ok ? ldg_pair(&p.tab[id[k]]) : make_longlong2(0, 0);
+            start[k] = e.x;
+            count[k] = e.y;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            live[k] = idx[k] < nreq;
+            live[k] = idx[k] < limit;
             badid[k] = false;
             start[k] = live[k] ? p.starts[idx[k]] : 0;
             count[k] = live[k] ? p.counts[idx[k]] : 0;
@@ -246,35 +282,56 @@ __device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
     }
     return v;
 }
+__device__ __forceinline__ int64_t warp_sum(int64_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
 
 struct GatherArgs {
     ddsk_var_t var;
-    const int64_t *starts;   // FIXED: start row per request
-    int64_t count;           // FIXED: rows per request
-    uint64_t *req_src; // VAR: planned source address (0 = skip)
-    int64_t *req_dst;  // VAR: [nreq+1] exclusive scan; req_dst[nreq] = total bytes
-    PlanSrc plan;      // VAR with fused_plan: where (start, count) of request i comes from
-    unsigned long long *tile_state; // VAR with fused_plan: one look-back word per 128-request tile
-    unsigned int epoch;             // tags tile_state words of THIS launch (no per-launch memset)
-    int fused_plan;
+    const int64_t *starts; // FIXED: start row per request
+    int64_t count;         // FIXED: rows per request
+    // VAR, plan in global scratch (large batches; written by the two plan kernels before this launch)
+    const uint64_t *req_src;  // planned source address (0 = skip)
+    const int64_t *req_dst;   // [nreq+1] exclusive scan; req_dst[nreq] = total bytes
+    const uint32_t *seg_tab;  // [T / SEG_GRAIN + 1] request covering byte k * SEG_GRAIN of the packed buffer
+    // VAR, plan in shared memory (<= PCAP requests): where (start, count) of request i comes from
+    PlanSrc plan;
+    int64_t *total_out; // VAR + shared plan: CTA 0 publishes the packed total here (one device word)
     int64_t nreq;
     char *dst;
     int64_t dst_cap;
-    int64_t *offsets_out; // FIXED: optional [nreq+1]
+    int64_t *offsets_out; // optional [nreq+1]
     unsigned long long *status;
-    unsigned int *counters;
+    unsigned int *counters; // [0] segment ticket, [1] finished warps -- self-resetting, ticketed launches only
     // multi-array batches (plan.nvars > 1): the packed result of variable v goes to mdst[v]
     char *mdst[DDSK_MAX_MULTI];
     int64_t mcap[DDSK_MAX_MULTI];
     int64_t *moffsets[DDSK_MAX_MULTI]; // optional per-variable [per_var + 1] byte offsets
-    int overlap;   // declared independent of its neighbours in the queue: segments are strided statically instead of
-                   // ticketed; a variable-count launch then works in its own scratch slot with monotonic counters
-    int skip_wait; // ... and the launch before it was one too: do not wait for it to finish
-    unsigned int ticket_base, tiles_base, finish_target; // VAR + overlap: values of the slot's monotonic counters
-                                                         // [2] (plan tickets), [3] (tiles done), [1] (warps finished)
-                                                         // after every earlier user of the slot
+    int min_seg_chunks;                // smallest segment, in chunks (claims cost more when the plan is in global memory)
+    // ---- overlap protocol (DDS_OVERLAP: a batch declared independent of the ONE batch queued right before it)
+    //   * segments are strided statically (no shared ticket state);
+    //   * launch q of a run may start while q-1 is still running (skip_wait: no griddepcontrol.wait), but
+    //     - it does not write a byte of caller-visible memory before launch q-2 has RETIRED (gate on done[q-2]):
+    //       a double-buffered queue that reuses the buffers of batch q-2 is safe whatever else occupies the GPU;
+    //     - its last warp publishes done[q] only after done[q-1] is published: launches retire in order, so whatever
+    //       the stream runs after launch q sees every earlier batch complete.
+    //   Every CTA of q-2 and q-1 has started before the first CTA of q can (programmatic launch order), so the waits
+    //   are on warps that are already running: no co-residency assumption, no deadlock.
+    //   * a variable-count launch planned by the plan kernels owns scratch slot q & 3; its lookup kernel skips the grid
+    //     wait too (so the PLAN of batch q runs under the gather of batch q-1) after checking that launch q-4, the
+    //     slot's previous user, has retired; the gather itself waits for its own plan kernels only.
+    int overlap, skip_wait;
+    int wait1_valid, wait2_valid; // q-1 / q-2 belong to the same run
+    unsigned int seq;             // q (per-store counter of overlap launches, wraps)
+    unsigned int *ovl;            // [0..3] finished-warp counters, [4..7] done words, slot = q & 3
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
+    unsigned long long *dbg;         // DDS_DEBUG_TIMING: per CTA [entry, plan done, first data, last warp done] (globaltimer ns)
 };
+
+// the walk's granularity for segment tables: segment sizes of variable-count launches are multiples of this
+constexpr int64_t SEG_GRAIN = 16384;
 
 // One pipeline stage carries a GROUP of up to 32 pieces (one per lane): consecutive requests of the walk, or one
 // <= CH-byte piece of a large request. Small requests therefore still put ~CH bytes in flight per stage.
@@ -285,14 +342,34 @@ struct Piece {
     uint32_t off;  // byte offset of this piece's aligned superset inside the stage
 };
 
-template <bool FIXED, int CH>
+// The plan as the walk sees it: request i's source address and packed offset.
+//   PCAP > 0: the CTA's own copy in shared memory (uint32 offsets: this path requires dst_cap < 4 GiB)
+//   PCAP = 0: global scratch written by the plan kernels
+template <int PCAP>
+struct PlanView {
+    uint32_t src_s, dst_s; // shared addresses of u64 src[PCAP], u32 dst[PCAP + 1]
+    __device__ __forceinline__ uint64_t s(int64_t i) const { return lds64(src_s + (uint32_t)i * 8u); }
+    __device__ __forceinline__ int64_t d(int64_t i) const { return (int64_t)lds32(dst_s + (uint32_t)i * 4u); }
+};
+template <>
+struct PlanView<0> {
+    const uint64_t *src;
+    const int64_t *dst;
+    const uint32_t *seg_tab;
+    __device__ __forceinline__ uint64_t s(int64_t i) const { return src[i]; }
+    __device__ __forceinline__ int64_t d(int64_t i) const { return dst[i]; }
+};
+
+template <bool FIXED, int CH, int PCAP>
 struct ChunkWalker {
     // warp-uniform state
     int64_t seg_pos = 0, seg_end = 0, T = 0, seg_bytes = 0, nseg = 0, nb = 0;
     int64_t gwarp = 0, nwarps = 1; // this warp's global index / warps in the grid (first segment = gwarp)
     bool first_claim = true, static_claims = false;
     int64_t cur_seg = 0;
+    unsigned int pend = 0; // lane 0: ticket claimed ahead of need (the atomic's latency hides behind the current segment)
     int64_t r = 0, win_base = -64;
+    PlanView<PCAP> pv;
     // per-lane window of 32 request descriptors
     uint64_t w_src = 0;
     int64_t w_dst = 0, w_n = 0;
@@ -313,20 +390,27 @@ struct ChunkWalker {
                 w_dst = idx * nb;
                 w_n = nb;
             } else {
-                w_src = a.req_src[idx];
-                w_dst = a.req_dst[idx];
-                w_n = a.req_dst[idx + 1] - w_dst;
+                w_src = pv.s(idx);
+                w_dst = pv.d(idx);
+                w_n = pv.d(idx + 1) - w_dst;
             }
         }
     }
 
-    // largest r in [0, nreq) with req_dst[r] <= pos, 32-ary search across the lanes
+    // largest r in [0, nreq) with dst[r] <= pos
     __device__ __forceinline__ int64_t locate_var(const GatherArgs &a, int64_t pos, int lane) {
-        int64_t lo = 0, hi = a.nreq;
+        if (PCAP == 0) {
+            // plan in global memory: the plan kernels left the answer for every SEG_GRAIN boundary (one load)
+            int64_t r0 = (int64_t)__ldg(&a.seg_tab[pos / SEG_GRAIN]);
+            // zero-length requests right after it share its end offset only if pos is their start too; the table holds
+            // the request whose bytes cover pos, which is the largest index with dst <= pos
+            return r0;
+        }
+        int64_t lo = 0, hi = a.nreq; // 32-ary search across the lanes, shared-memory reads
         while (hi - lo > 1) {
             int64_t step = (hi - lo + 31) / 32;
             int64_t idx = lo + (int64_t)(lane + 1) * step;
-            bool le = (idx < hi) && (a.req_dst[idx] <= pos);
+            bool le = (idx < hi) && (pv.d(idx) <= pos);
             int k = __popc(__ballot_sync(0xffffffffu, le));
             lo = lo + (int64_t)k * step;
             hi = min(hi, lo + step);
@@ -340,17 +424,18 @@ struct ChunkWalker {
         while (true) {
             if (seg_pos >= seg_end) {
                 // the first segment of warp g is segment g (no ticket: spares ~1800 same-address atomics at the
-                // start of every launch); later ones come from the ticket counter, offset by the warp count
+                // start of every launch); later ones come from the ticket counter, offset by the warp count. The
+                // ticket for the segment AFTER this one is requested now and read at the next claim.
                 int64_t seg;
                 if (first_claim) {
                     first_claim = false;
                     seg = gwarp;
+                    if (!static_claims && seg < nseg && lane == 0) pend = atomicAdd(&a.counters[0], 1u);
                 } else if (static_claims) {
                     seg = cur_seg + nwarps; // overlapped launches share no mutable state: plain striding
                 } else {
-                    unsigned int t = 0;
-                    if (lane == 0) t = atomicAdd(&a.counters[0], 1u);
-                    seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+                    seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, pend, 0);
+                    if (seg < nseg && lane == 0) pend = atomicAdd(&a.counters[0], 1u);
                 }
                 cur_seg = seg;
                 if (seg >= nseg) return 0;
@@ -489,171 +574,148 @@ __device__ __forceinline__ void drain_chunk(uint32_t sb, uint32_t a, char *d, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused plan (variable counts): the lookup + checks + exclusive scan of request sizes run INSIDE the gather
-// launch. Warps take 128-request tiles by ticket; a tile's offset comes from a decoupled look-back over the
-// tiles before it (each lane polls one predecessor). Tiles are ticketed in running order, so a tile only ever
-// waits for tiles held by warps that are already running: no co-residency assumption, no deadlock.
+// Plan in shared memory (variable counts, <= PCAP requests): EVERY CTA computes the whole plan -- lookup + checks +
+// exclusive scan of the request sizes -- for itself. The index arrays are a few tens of KB that stay in L2 after
+// the first CTA touched them, so the redundancy costs ~1 us, and it removes every inter-CTA dependency the plan
+// used to have (tile tickets, look-back, a grid-wide "all tiles written" wait) as well as the L2 round trips of the
+// walk's searches and descriptor loads. Warp w owns a contiguous run of requests; loads are coalesced (lane-strided).
+// Returns the packed total T (exact, int64); the shared copy keeps 32-bit offsets (the launcher uses this path only
+// when the destination capacity is below 4 GiB, so T > 2^32 is a capacity error and nothing is copied).
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE_ITEMS = 4;
-constexpr int TILE_REQ = 32 * TILE_ITEMS;
-
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// tile_state word: [63:42] epoch (22 bits) | [41:40] flag (1 = aggregate, 2 = inclusive prefix) | [39:0] bytes
-__device__ __forceinline__ unsigned long long tile_pack(unsigned int epoch, unsigned int flag, int64_t v) {
-    return ((unsigned long long)(epoch & 0x3FFFFFu) << 42) | ((unsigned long long)flag << 40) |
-           ((unsigned long long)v & 0xFFFFFFFFFFull);
-}
-
-__device__ __forceinline__ void plan_in_kernel(const GatherArgs &a, int lane) {
-    const int64_t ntiles = (a.nreq + TILE_REQ - 1) / TILE_REQ;
-    while (true) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(&a.counters[2], 1u) - a.ticket_base; // base = 0 for self-resetting counters
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if ((int64_t)tile >= ntiles) break; // (every warp makes exactly one failing claim: the host counts on that)
-        // lane owns TILE_ITEMS consecutive requests
-        int64_t idx[TILE_ITEMS], nb[TILE_ITEMS];
-        uint64_t sv[TILE_ITEMS];
+template <int NW, int PCAP>
+__device__ __forceinline__ int64_t plan_in_smem(const GatherArgs &a, const PlanView<PCAP> &pv, int64_t *wtot, int warp,
+                                                int lane, bool writer) {
+    const int64_t nreq = a.nreq;
+    const int64_t per_warp = ((nreq + NW * 128 - 1) / (NW * 128)) * 128;
+    const int64_t w0 = min(nreq, (int64_t)warp * per_warp), w1 = min(nreq, w0 + per_warp);
+    int64_t lane_sum = 0;
+    for (int64_t b = w0; b < w1; b += 128) {
+        int64_t idx[4], nb[4];
+        uint64_t sv[4];
 #pragma unroll
-        for (int k = 0; k < TILE_ITEMS; k++) idx[k] = (int64_t)tile * TILE_REQ + lane * TILE_ITEMS + k;
-        plan_many<TILE_ITEMS>(a.var, a.plan, idx, a.nreq, a.status, sv, nb);
-        int64_t mine = 0;
+        for (int k = 0; k < 4; k++) idx[k] = b + k * 32 + lane;
+        plan_many<4>(a.var, a.plan, idx, w1, a.status, sv, nb);
 #pragma unroll
-        for (int k = 0; k < TILE_ITEMS; k++) mine += nb[k];
-        const int64_t incl = warp_incl_scan(mine, lane);
-        const int64_t agg = __shfl_sync(0xffffffffu, incl, 31);
-        // publish the aggregate, then look back
-        if (lane == 0) st_release_u64(&a.tile_state[tile], tile_pack(a.epoch, tile == 0 ? 2u : 1u, agg));
-        int64_t excl = 0;
-        if (tile > 0) {
-            int64_t base = (int64_t)tile - 1;
-            while (true) {
-                const int64_t t = base - lane; // lane 0 polls the nearest predecessor
-                unsigned long long wv = tile_pack(a.epoch, 2u, 0);
-                if (t >= 0) {
-                    const uint64_t t0 = globaltimer_ns();
-                    do {
-                        wv = ld_acquire_u64(&a.tile_state[t]);
-                        if (globaltimer_ns() - t0 > 4000000000ull) { // never expected; do not hang the box
-                            report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
-                            __trap();
-                        }
-                    } while ((unsigned int)(wv >> 42) != (a.epoch & 0x3FFFFFu) || ((wv >> 40) & 3u) == 0);
-                }
-                const unsigned int flag = (unsigned int)((wv >> 40) & 3u);
-                const int64_t val = (int64_t)(wv & 0xFFFFFFFFFFull);
-                const unsigned inc = __ballot_sync(0xffffffffu, flag == 2u);
-                const int stop = inc ? __ffs(inc) - 1 : 31; // nearest tile that already knows its inclusive prefix
-                int64_t c = lane <= stop ? val : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                excl += c;
-                if (inc) break;
-                base -= 32;
-            }
-            if (lane == 0) st_release_u64(&a.tile_state[tile], tile_pack(a.epoch, 2u, excl + agg));
-        }
-        int64_t run = excl + incl - mine;
-#pragma unroll
-        for (int k = 0; k < TILE_ITEMS; k++) {
-            if (idx[k] < a.nreq) {
-                a.req_src[idx[k]] = sv[k];
-                a.req_dst[idx[k]] = run;
-                if (a.offsets_out) a.offsets_out[idx[k]] = run;
-                run += nb[k];
-            }
-        }
-        if ((int64_t)tile == ntiles - 1 && lane == 31) {
-            a.req_dst[a.nreq] = excl + agg;
-            if (a.offsets_out) a.offsets_out[a.nreq] = excl + agg;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            atomicAdd(&a.counters[3], 1u);
-        }
-    }
-    // every tile has an owner that is running; wait until all of them have written their part of the plan
-    if (lane == 0) {
-        const uint64_t t0 = globaltimer_ns();
-        while ((int64_t)(unsigned int)(ld_acquire_u32(&a.counters[3]) - a.tiles_base) < ntiles) {
-            __nanosleep(200);
-            if (globaltimer_ns() - t0 > 4000000000ull) {
-                report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
-                __trap();
+        for (int k = 0; k < 4; k++) {
+            if (idx[k] < w1) {
+                sts64(pv.src_s + (uint32_t)idx[k] * 8u, sv[k]);
+                sts32(pv.dst_s + (uint32_t)idx[k] * 4u, (uint32_t)min(nb[k], (int64_t)0xFFFFFFFFll)); // size, for pass 2
+                lane_sum += nb[k];
             }
         }
     }
-    __syncwarp();
+    const int64_t wsum = warp_sum(lane_sum);
+    if (lane == 0) wtot[warp] = wsum;
+    __syncthreads();
+    int64_t mine = lane < NW ? wtot[lane] : 0;
+    const int64_t T = warp_sum(mine);
+    const int64_t base = warp_sum(lane < warp ? mine : 0);
+    // pass 2: exclusive scan of this warp's run, in place
+    int64_t run = base;
+    for (int64_t b = w0; b < w1; b += 32) {
+        const int64_t i = b + lane;
+        const int64_t v = i < w1 ? (int64_t)lds32(pv.dst_s + (uint32_t)i * 4u) : 0;
+        const int64_t incl = warp_incl_scan(v, lane);
+        if (i < w1) {
+            sts32(pv.dst_s + (uint32_t)i * 4u, (uint32_t)(run + incl - v));
+            if (writer && a.offsets_out) a.offsets_out[i] = run + incl - v;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (warp == 0 && lane == 0) {
+        sts32(pv.dst_s + (uint32_t)nreq * 4u, (uint32_t)min(T, (int64_t)0xFFFFFFFFll));
+        if (writer) {
+            if (a.offsets_out) a.offsets_out[nreq] = T;
+            if (a.total_out) *a.total_out = T;
+        }
+    }
+    __syncthreads();
+    return T;
 }
 
-template <bool FIXED, int NW, int S, int CH>
+struct PieceDesc {
+    int64_t dpos;
+    uint32_t n, pack; // pack = stage offset | (source misalignment << 16)
+};
+
+// wait until overlap launch q has retired (its done word carries a sequence number >= q)
+__device__ __forceinline__ void spin_until_done(const unsigned int *ovl, unsigned int q, unsigned long long *status, int64_t nreq) {
+    const uint64_t t0 = globaltimer_ns();
+    while ((int)(ld_acquire_u32(&ovl[4 + (q & 3u)]) - q) < 0) {
+        __nanosleep(100);
+        if (globaltimer_ns() - t0 > 4000000000ull) { // never expected; do not hang the box
+            report(status, nreq, DDSK_CODE_WATCHDOG);
+            __trap();
+        }
+    }
+}
+
+template <bool FIXED, int NW, int S, int CH, int PCAP>
 __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_constant__ GatherArgs a) {
     constexpr int STAGE = CH + 32; // room for the aligned superset of a misaligned CH-byte range
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[NW][S];
-    __shared__ __align__(16) struct PieceDesc {
-        int64_t dpos;
-        uint32_t n, pack; // pack = stage offset | (source misalignment << 16)
-    } desc[NW][S][32];
+    __shared__ __align__(16) PieceDesc desc[NW][S][32];
+    __shared__ int64_t wtot[PCAP > 0 ? NW : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t gwarp = (int64_t)blockIdx.x * NW + warp;
     const int64_t nwarps = (int64_t)gridDim.x * NW;
 
-    // Programmatic dependent launch: let the NEXT kernel of the stream start launching right away (its CTAs
-    // take over each SM as ours retire), and do not touch global memory before the PREVIOUS kernel (which may
-    // have produced our indices / plan, and resets the ticket counters) has completed and flushed.
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[warp][s]), 1);
         fence_mbar_init();
     }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // An overlapped batch shares nothing with the launches before it (own destination, indices already in place,
-    // no ticket counters), so its CTAs start moving bytes as soon as an SM frees up: the tail of batch k and the
-    // head of batch k+1 overlap, whatever else is running on the GPU.
-    // (The first batch of such a run still waits, so a ticketed launch before the run has retired for good before
-    // any ticketed launch after the run can start.)
-    if (!a.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!FIXED && a.overlap) {
-        // the scratch slot of an overlapped variable-count batch is reused every few launches: its previous user must
-        // have retired completely (all of ITS CTAs have started long ago, so this cannot deadlock)
-        if (lane == 0) {
-            const uint64_t t0 = globaltimer_ns();
-            while ((int)(ld_acquire_u32(&a.counters[1]) - a.finish_target) < 0) {
-                __nanosleep(100);
-                if (globaltimer_ns() - t0 > 4000000000ull) {
-                    report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
-                    __trap();
-                }
-            }
+    if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 4 + 0] = globaltimer_ns();
+    // Programmatic dependent launch: let the NEXT kernel of the stream start launching early (its CTAs take over each
+    // SM as ours retire), and do not touch global memory before the PREVIOUS kernel (which may have produced our
+    // indices / plan, and resets the ticket counters) has completed and flushed.
+    // The first launch of an overlap run triggers only AFTER its own wait: its successor skips the wait, and must not
+    // be able to start while anything older than this launch is still in flight.
+    if (a.overlap && !a.wait1_valid) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    } else {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (!a.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    // gate of the overlap protocol: no caller-visible byte is written before launch q-2 has retired
+    bool gate_open = !(a.overlap && a.wait2_valid);
+    auto pass_gate = [&]() {
+        if (!gate_open) {
+            if (lane == 0) spin_until_done(a.ovl, a.seq - 2u, a.status, a.nreq);
+            __syncwarp();
+            gate_open = true;
+        }
+    };
+
+    // ---- the plan (variable counts) ------------------------------------------------------------
+    ChunkWalker<FIXED, CH, PCAP> w;
+    if (!FIXED) {
+        if constexpr (PCAP > 0) {
+            w.pv.src_s = smem_u32(smem_dyn) + (uint32_t)(NW * S * STAGE);
+            w.pv.dst_s = w.pv.src_s + (uint32_t)PCAP * 8u;
+            const bool writer = blockIdx.x == 0;
+            if (writer) pass_gate(); // CTA 0 writes the offsets / the total for the caller
+            w.T = plan_in_smem<NW, PCAP>(a, w.pv, wtot, warp, lane, writer);
+        } else {
+            w.pv.src = a.req_src;
+            w.pv.dst = a.req_dst;
+            w.pv.seg_tab = a.seg_tab;
+            w.T = *(volatile const int64_t *)&a.req_dst[a.nreq];
         }
     }
-    __syncwarp();
 
-    if (!FIXED && a.fused_plan) plan_in_kernel(a, lane);
-
+    if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
+    bool dbg_first = a.dbg != nullptr && warp == 0;
     // ---- total bytes, segment geometry -------------------------------------------------------
-    ChunkWalker<FIXED, CH> w;
     w.gwarp = gwarp;
     w.nwarps = nwarps;
     w.static_claims = a.overlap != 0;
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
-    w.T = FIXED ? w.nb * a.nreq : *(volatile const int64_t *)&a.req_dst[a.nreq];
+    if (FIXED) w.T = w.nb * a.nreq;
     bool over = w.T > a.dst_cap;
     // multi-array batch: the walk runs over the concatenation of the variables' packed results; vbase[v] is where
     // variable v starts in that virtual space (unused slots are +inf so dst_of() never selects them)
@@ -665,13 +727,14 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         over = false;
 #pragma unroll
         for (int v = 0; v < DDSK_MAX_MULTI; v++)
-            if (v < a.plan.nvars) vbase[v] = *(volatile const int64_t *)&a.req_dst[(int64_t)v * a.plan.per_var];
+            if (v < a.plan.nvars) vbase[v] = w.pv.d((int64_t)v * a.plan.per_var);
 #pragma unroll
         for (int v = 0; v < DDSK_MAX_MULTI; v++)
             if (v < a.plan.nvars) {
                 const int64_t endv = v + 1 < a.plan.nvars ? vbase[v + 1] : w.T;
                 over |= endv - vbase[v] > a.mcap[v];
             }
+        if (PCAP > 0) over |= w.T > 0xFFFFFFFFll; // 32-bit shared offsets
     }
     auto dst_of = [&](int64_t dpos) -> char * {
         if (!multi) return a.dst + dpos;
@@ -686,15 +749,17 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         return d + (dpos - b);
     };
     {
-        // FIXED: a claim is one atomic + a division, so small segments (8 per warp) keep the tail short.
-        // VAR: every claim also costs a 32-ary search over req_dst (2-3 dependent L2 round trips), so segments are
-        // at least 4 chunks (measured: config 3 at B=4096 47.6 -> 41.8 us).
+        // A claim is one atomic (requested ahead of need) + a division (FIXED), a shared-memory search (VAR, plan in
+        // shared memory) or one global load (VAR, plan in global scratch). Small segments (8 per warp) keep the tail
+        // short; variable-count segments are multiples of SEG_GRAIN when the segment table is in use.
         int64_t target = w.T / (nwarps * 8);
-        target = max((int64_t)(FIXED ? CH : 4 * CH), min(target, (int64_t)1 << 20));
+        const int64_t unit = (!FIXED && PCAP == 0) ? SEG_GRAIN : (int64_t)CH;
+        target = max((int64_t)a.min_seg_chunks * CH, min(target, (int64_t)1 << 20));
+        target = max(target, unit);
         if (FIXED && w.nb > 0 && w.nb <= target)
             w.seg_bytes = (target / w.nb) * w.nb; // whole requests per segment
         else
-            w.seg_bytes = (target / CH) * CH;
+            w.seg_bytes = (target / unit) * unit;
         w.nseg = w.T > 0 ? (w.T + w.seg_bytes - 1) / w.seg_bytes : 0;
     }
     if (over) {
@@ -702,9 +767,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         w.nseg = 0;
     }
 
-    // ---- FIXED with nothing to walk (count == 0, or the batch does not fit): run the reference's two checks here,
+    // ---- FIXED with nothing to walk (count <= 0, or the batch does not fit): run the reference's two checks here,
     //      so an invalid request is still the error that gets reported
-    if (FIXED && (w.nb == 0 || over)) {
+    if (FIXED && (w.nb <= 0 || over)) {
         for (int64_t i = gwarp * 32 + lane; i < a.nreq; i += nwarps * 32) {
             uint64_t s;
             int code = dev_locate(a.var, a.starts[i], a.count, &s);
@@ -756,6 +821,11 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             }
         }
         __syncwarp();
+        if (dbg_first) {
+            dbg_first = false;
+            if (lane == 0) a.dbg[blockIdx.x * 4 + 2] = globaltimer_ns();
+        }
+        pass_gate(); // overlap protocol: the loads above were harmless, the stores below are not
         const int64_t my_dpos = desc[warp][st][lane].dpos;
         const uint32_t my_n = desc[warp][st][lane].n;
         const uint32_t my_pack = desc[warp][st][lane].pack;
@@ -778,16 +848,23 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         __syncwarp();  // all lanes are done reading the stage before it is refilled
         consumed++;
     }
-    bulk_wait_read<0>(); // every lane: its stages have been read out; the global writes complete with the grid
+    if (a.overlap) {
+        bulk_wait_all<0>(); // every lane: its bulk stores have been performed (the done word below promises that)
+        fence_proxy_async_global();
+    } else {
+        bulk_wait_read<0>(); // every lane: its stages have been read out; the global writes complete with the grid
+    }
     __syncwarp();
+    pass_gate();
     if (multi) { // per-variable byte offsets = plan offsets rebased to the variable's start
         for (int64_t i = gwarp * 32 + lane; i < a.nreq + a.plan.nvars; i += nwarps * 32) {
             // entry (v, j) for j in [0, per_var]: i enumerates nvars * (per_var + 1) slots
             const int v = (int)(i / (a.plan.per_var + 1));
             const int64_t j = i - (int64_t)v * (a.plan.per_var + 1);
             if (v < a.plan.nvars && a.moffsets[v]) {
-                const int64_t basev = a.req_dst[(int64_t)v * a.plan.per_var]; // == vbase[v]; read from memory so that
-                a.moffsets[v][j] = a.req_dst[(int64_t)v * a.plan.per_var + j] - basev; // vbase[] is never indexed dynamically
+                const int64_t basev = w.pv.d((int64_t)v * a.plan.per_var); // == vbase[v]; re-read so that vbase[] is
+                int64_t e = (v * a.plan.per_var + j == a.nreq) ? w.T : w.pv.d((int64_t)v * a.plan.per_var + j);
+                a.moffsets[v][j] = e - basev;                                // never indexed dynamically
             }
         }
     }
@@ -795,19 +872,27 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
     }
 
-    if (!FIXED && a.overlap && lane == 0) { // this warp is done with the slot's plan arrays
-        __threadfence();
-        atomicAdd(&a.counters[1], 1u);
-    }
-    // ---- self-resetting ticket counters (not used by overlapped launches) ---------------------
-    if (lane == 0 && !a.overlap) {
+    if (a.dbg && lane == 0) atomicMax(&a.dbg[blockIdx.x * 4 + 3], (unsigned long long)globaltimer_ns());
+    if (a.overlap) {
+        // ---- overlap protocol: retire in order
+        if (lane == 0) {
+            __threadfence();
+            const unsigned int slot = a.seq & 3u;
+            const unsigned int done = atomicAdd(&a.ovl[slot], 1u);
+            if (done == (unsigned int)(nwarps - 1)) {
+                a.ovl[slot] = 0;
+                if (a.wait1_valid) spin_until_done(a.ovl, a.seq - 1u, a.status, a.nreq);
+                __threadfence();
+                st_release_u32(&a.ovl[4 + slot], a.seq);
+            }
+        }
+    } else if (lane == 0) {
+        // ---- self-resetting ticket counters
         __threadfence();
         unsigned int done = atomicAdd(&a.counters[1], 1u);
         if (done == (unsigned int)(nwarps - 1)) {
             a.counters[0] = 0;
             a.counters[1] = 0;
-            a.counters[2] = 0;
-            a.counters[3] = 0;
             __threadfence();
             if (a.host_mirror) { // the last warp publishes status + total straight into pinned host memory: the host
                                  // reads them after the stream sync, no D2H copy in the call
@@ -820,14 +905,52 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// plan kernels (variable counts): lookup + checks + exclusive scan of request bytes
+// dds_small_get_kernel: ONE request, ONE CTA -- the legacy one-get()-per-sample loop (include/ddstore.hpp:197-238
+// driven by examples/vae/distdataset.py:79-92). A 148-CTA persistent launch costs ~6 us of ramp/retire for a few KB;
+// this one is a plain copy loop that also does the reference's checks, writes the payload (device memory, or pinned
+// host memory zero-copy) and then a completion word the host spins on -- no stream synchronize in the call.
+// flag[0] = status word ((bad << 8) | code, or DDSK_STATUS_OK), flag[1] = bytes, flag[2] = ticket (written last).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dds_small_get_kernel(const __grid_constant__ ddsk_var_t var, int64_t start, int64_t count,
+                                                            char *__restrict__ dst, int64_t dst_cap,
+                                                            volatile unsigned long long *flag, unsigned long long ticket) {
+    uint64_t src = 0;
+    const int code = dev_locate(var, start, count, &src);
+    const int64_t n = code ? 0 : count * var.row_bytes;
+    unsigned long long st = DDSK_STATUS_OK;
+    if (code) st = (unsigned long long)code;                   // request 0
+    else if (n > dst_cap) st = ((unsigned long long)1 << 8) | DDSK_CODE_CAPACITY; // index 1 = nreq, like the batch kernel
+    if (st == DDSK_STATUS_OK && n > 0) {
+        const char *s = (const char *)src;
+        if ((((uint64_t)s | (uint64_t)dst | (uint64_t)n) & 15u) == 0) {
+            const uint4 *s4 = (const uint4 *)s;
+            uint4 *d4 = (uint4 *)dst;
+            for (int64_t i = threadIdx.x; i < (n >> 4); i += blockDim.x) d4[i] = s4[i];
+        } else if ((((uint64_t)s | (uint64_t)dst | (uint64_t)n) & 3u) == 0) {
+            const uint32_t *s1 = (const uint32_t *)s;
+            uint32_t *d1 = (uint32_t *)dst;
+            for (int64_t i = threadIdx.x; i < (n >> 2); i += blockDim.x) d1[i] = s1[i];
+        } else {
+            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        flag[0] = st;
+        flag[1] = (unsigned long long)n;
+        __threadfence_system();
+        flag[2] = ticket;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan kernels (variable counts, batches too large for the shared-memory plan): lookup + checks + exclusive scan of
+// request bytes into global scratch, plus the segment table the walk's claims read
 // ------------------------------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 256;
 constexpr int PLAN_ITEMS = 4;
 constexpr int PLAN_TILE = PLAN_THREADS * PLAN_ITEMS;
-constexpr int PLAN1_THREADS = 1024; // single-CTA plan for small batches
-constexpr int PLAN1_ITEMS = 8;
-constexpr int PLAN1_MAX = PLAN1_THREADS * PLAN1_ITEMS;
 
 // block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, *total = block sum
 template <int NT>
@@ -849,56 +972,25 @@ __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
     return base + inc - v;
 }
 
-// small batches (<= 8192 requests): the whole plan in ONE CTA, one launch
-__global__ void __launch_bounds__(PLAN1_THREADS) dds_plan_single_kernel(const __grid_constant__ ddsk_var_t var,
-                                                                        const __grid_constant__ PlanSrc p, int64_t nreq,
-                                                                        uint64_t *__restrict__ req_src,
-                                                                        int64_t *__restrict__ req_dst,
-                                                                        int64_t *__restrict__ offsets_out,
-                                                                        unsigned long long *status) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    // blocked: thread t owns the ipt (<= 8) consecutive requests [t*ipt, (t+1)*ipt), so every thread has work
-    const int ipt = (int)((nreq + PLAN1_THREADS - 1) / PLAN1_THREADS);
-    const int64_t base = (int64_t)threadIdx.x * ipt;
-    int64_t idx[PLAN1_ITEMS], nb[PLAN1_ITEMS];
-    uint64_t sv[PLAN1_ITEMS];
-#pragma unroll
-    for (int k = 0; k < PLAN1_ITEMS; k++) idx[k] = k < ipt ? base + k : nreq;
-    plan_many<PLAN1_ITEMS>(var, p, idx, nreq, status, sv, nb);
-    int64_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < PLAN1_ITEMS; k++) {
-        if (idx[k] < nreq) {
-            req_src[idx[k]] = sv[k];
-            mine += nb[k];
-        }
-    }
-    int64_t tot;
-    int64_t run = block_excl_scan<PLAN1_THREADS>(mine, &tot);
-#pragma unroll
-    for (int k = 0; k < PLAN1_ITEMS; k++) {
-        if (idx[k] < nreq) {
-            req_dst[idx[k]] = run;
-            if (offsets_out) offsets_out[idx[k]] = run;
-            run += nb[k];
-        }
-    }
-    if (threadIdx.x == 0) {
-        req_dst[nreq] = tot;
-        if (offsets_out) offsets_out[nreq] = tot;
-    }
-}
+// pass 1: per request source address + byte size (size parked in req_dst), per tile byte sum
+struct PlanProto { // overlap protocol as the plan kernels see it (all zero: ordinary launch)
+    const unsigned int *ovl;
+    unsigned int seq;
+    int skip_wait, wait2_valid, wait4_valid;
+};
 
-// pass 1 (large batches): per request source address + byte size (size parked in req_dst), per tile byte sum
 __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __grid_constant__ ddsk_var_t var,
                                                                        const __grid_constant__ PlanSrc p, int64_t nreq,
                                                                        uint64_t *__restrict__ req_src,
                                                                        int64_t *__restrict__ req_dst,
                                                                        int64_t *__restrict__ tile_sums,
-                                                                       unsigned long long *status) {
+                                                                       unsigned long long *status, PlanProto pr) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!pr.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (pr.wait4_valid) { // the scratch slot's previous user (launch seq-4) must have retired before it is overwritten
+        if (threadIdx.x == 0) spin_until_done(pr.ovl, pr.seq - 4u, status, nreq);
+        __syncthreads();
+    }
     const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
     int64_t idx[PLAN_ITEMS], nb[PLAN_ITEMS];
     uint64_t sv[PLAN_ITEMS];
@@ -919,12 +1011,20 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __g
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
-// pass 2: exclusive scan. Each CTA sums the tiles before it, then scans its own tile in place.
+// pass 2: exclusive scan. Each CTA sums the tiles before it, then scans its own tile in place, and notes in the
+// segment table which request covers every SEG_GRAIN boundary of the packed buffer that falls inside its requests
+// (so a segment claim of the gather is one load instead of a search over req_dst).
 __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nreq, int64_t *__restrict__ req_dst,
                                                                      const int64_t *__restrict__ tile_sums,
-                                                                     int64_t *__restrict__ offsets_out) {
+                                                                     int64_t *__restrict__ offsets_out,
+                                                                     uint32_t *__restrict__ seg_tab, int64_t seg_cap,
+                                                                     unsigned long long *status, PlanProto pr) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory"); // the lookup kernel of this batch
+    if (pr.wait2_valid && offsets_out) { // offsets are caller-visible: not before launch seq-2 has retired
+        if (threadIdx.x == 0) spin_until_done(pr.ovl, pr.seq - 2u, status, nreq);
+        __syncthreads();
+    }
     int64_t part = 0;
     for (int64_t t = threadIdx.x; t < (int64_t)blockIdx.x; t += PLAN_THREADS) part += tile_sums[t];
     int64_t tile_base;
@@ -939,8 +1039,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nre
         int64_t tot;
         int64_t ex = block_excl_scan<PLAN_THREADS>(v, &tot);
         if (i < nreq) {
-            req_dst[i] = running + ex;
-            if (offsets_out) offsets_out[i] = running + ex;
+            const int64_t d0 = running + ex, d1 = d0 + v;
+            req_dst[i] = d0;
+            if (offsets_out) offsets_out[i] = d0;
+            for (int64_t g = (d0 + SEG_GRAIN - 1) / SEG_GRAIN; g * SEG_GRAIN < d1 && g < seg_cap; g++) seg_tab[g] = (uint32_t)i;
         }
         running += tot;
     }
@@ -951,7 +1053,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nre
 }
 
 // ------------------------------------------------------------------------------------------------
-// synthetic payload generator (bench / test helper)
+// synthetic payload generator + its on-device verifier (bench / test helpers)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -966,26 +1068,78 @@ __global__ void dds_synth_kernel(T *__restrict__ base, uint64_t first_elem, uint
         base[i] = (T)splitmix64(seed ^ (first_elem + i));
 }
 
+// Check a packed batch against the generator: request i = rows [starts[i], starts[i] + count_i) of a variable filled by
+// dds_synth_kernel with `seed`; its bytes sit at packed + (offsets ? offsets[i] : i * fixed_count * disp * itemsize).
+// out[0] += mismatching elements, out[1] += rows checked, out[2 + owner] += requests served by that owner.
+template <typename T>
+__global__ void dds_verify_kernel(const __grid_constant__ ddsk_var_t var, const unsigned char *__restrict__ packed,
+                                  const int64_t *__restrict__ starts, const int64_t *__restrict__ counts, int64_t fixed_count,
+                                  const int64_t *__restrict__ offsets, int64_t nreq, int64_t disp, uint64_t seed,
+                                  unsigned long long *out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long bad = 0, rows = 0;
+    for (int64_t i = gw; i < nreq; i += nw) {
+        const int64_t start = starts[i], cnt = counts ? counts[i] : fixed_count;
+        if (cnt <= 0) continue;
+        const int64_t off = offsets ? offsets[i] : i * fixed_count * disp * (int64_t)sizeof(T);
+        const T *p = (const T *)(packed + off);
+        const uint64_t e0 = (uint64_t)start * (uint64_t)disp, ne = (uint64_t)cnt * (uint64_t)disp;
+        for (uint64_t e = lane; e < ne; e += 32) bad += p[e] != (T)splitmix64(seed ^ (e0 + e));
+        if (lane == 0) {
+            rows += (unsigned long long)cnt;
+            atomicAdd(&out[2 + dev_sortedsearch(var, start)], 1ull);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, d);
+    if (lane == 0) {
+        if (bad) atomicAdd(&out[0], bad);
+        if (rows) atomicAdd(&out[1], rows);
+    }
+}
+
+// Test helper: hold `gridDim.x` SMs' worth of shared memory busy for `ns` nanoseconds (a stand-in for a training kernel
+// that shares the GPU with a prefetch queue; tests/test_gpu_parity.py uses it to attack the overlap protocol).
+__global__ void dds_occupy_kernel(unsigned long long ns) {
+    extern __shared__ unsigned char occ_smem[];
+    occ_smem[threadIdx.x] = (unsigned char)threadIdx.x;
+    const uint64_t t0 = globaltimer_ns();
+    while (globaltimer_ns() - t0 < ns) __nanosleep(1000);
+    if (occ_smem[threadIdx.x] == 255 && ns == 0) printf("");
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch geometry
 // ------------------------------------------------------------------------------------------------
 struct Geometry {
-    int nw, stages, ch;
+    int nw, stages, ch, pcap;
 };
-constexpr Geometry kGeoms[] = {{8, 4, 4096}, {8, 6, 4096}, {16, 3, 4096}, {4, 4, 8192}, {12, 4, 4096}, {4, 6, 4096}};
+// plan-in-global variants (fixed-count entry, and variable-count batches above 8192 requests)
+constexpr Geometry kGeoms[] = {{8, 4, 4096, 0}, {8, 6, 4096, 0}, {16, 3, 4096, 0}, {4, 4, 8192, 0}, {12, 4, 4096, 0}, {4, 6, 4096, 0}};
 constexpr int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
+// plan-in-shared-memory variants (variable-count entry): the plan's 12 B per request come out of the stage budget
+constexpr Geometry kGeomsS[] = {{12, 3, 4096, 4096}, {12, 3, 3072, 8192}, {16, 3, 2048, 8192}, {16, 3, 3072, 4096}, {8, 4, 4096, 4096}};
+constexpr int kNumGeomsS = (int)(sizeof(kGeomsS) / sizeof(kGeomsS[0]));
+constexpr int64_t kPlanSmemMax = 8192;
+// Measured (profiles/r2_timing_probe.md): the redundant plan costs 8.6 us at 4096 requests (19 us with sample-index
+// lookups: 148 SMs hammer the same lines), the plan kernels ~11 us serialised but ~0 when they run under the previous
+// batch's gather -- so by default only small batches, where one launch beats three, plan in shared memory.
+int64_t g_plan_smem_default = 1024; // DDS_SMEM_PLAN_MAX
 
 // Measured on B200 (profiles/r1_configs.md): 12 warps x 4 stages is as fast as 8 x 4 on 4 KiB+ rows and clearly
 // faster on the instruction-heavier variable / re-phase path; rows under 2 KiB want even more warps (16 x 3).
 constexpr int kGeomLarge = 4, kGeomSmall = 2, kGeomVar = 4;
 
 int g_geom_fixed_env = -1; // DDS_GATHER_GEOM      (tuning: force one variant for the fixed-count entry)
-int g_geom_var_env = -1;   // DDS_GATHER_GEOM_VAR  (... for the variable-count entry; defaults to the former)
+int g_geom_var_env = -1;   // DDS_GATHER_GEOM_VAR  (... for the variable-count entry, plan in global; defaults to the former)
+int g_geom_s_env = -1;     // DDS_GATHER_GEOM_S    (... for the variable-count entry, plan in shared memory)
+int g_min_seg_var = 4, g_min_seg_s = 2; // DDS_VAR_MINSEG / DDS_S_MINSEG: smallest segment in chunks
 bool g_geom_init = false;
 int g_sms = 0;
 int g_ctas_per_sm = 1;
 int g_pdl = 1;
-int g_fused_plan = 1; // DDS_FUSED_PLAN: 1 = auto (fused for <= 8192 requests), 0 = never, 2 = always (A/B switch)
+unsigned long long *g_dbg = nullptr; // DDS_DEBUG_TIMING=1: device buffer of per-CTA timestamps of the LAST gather launch
+int g_smem_plan = 1; // DDS_SMEM_PLAN: 1 = plan in shared memory when it fits (default), 0 = always the plan kernels (A/B switch)
 
 int pick_geometry() {
     if (g_geom_init) return 0;
@@ -997,9 +1151,19 @@ int pick_geometry() {
     g_geom_var_env = g_geom_fixed_env;
     if (const char *e = getenv("DDS_GATHER_GEOM_VAR")) g_geom_var_env = atoi(e);
     if (g_geom_var_env >= kNumGeoms) g_geom_var_env = -1;
+    if (const char *e = getenv("DDS_GATHER_GEOM_S")) g_geom_s_env = atoi(e);
+    if (g_geom_s_env >= kNumGeomsS) g_geom_s_env = -1;
+    if (const char *e = getenv("DDS_VAR_MINSEG")) g_min_seg_var = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char *e = getenv("DDS_S_MINSEG")) g_min_seg_s = atoi(e) > 0 ? atoi(e) : 2;
     if (const char *e = getenv("DDS_GATHER_CTAS_PER_SM")) g_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
-    if (const char *e = getenv("DDS_FUSED_PLAN")) g_fused_plan = atoi(e);
+    if (const char *e = getenv("DDS_SMEM_PLAN")) g_smem_plan = atoi(e);
+    if (const char *e = getenv("DDS_SMEM_PLAN_MAX")) g_plan_smem_default = atoll(e);
+    if (const char *e = getenv("DDS_DEBUG_TIMING"))
+        if (atoi(e)) {
+            CUDA_TRY(cudaMalloc((void **)&g_dbg, 1024 * 4 * 8));
+            CUDA_TRY(cudaMemset(g_dbg, 0, 1024 * 4 * 8));
+        }
     g_geom_init = true;
     return 0;
 }
@@ -1011,20 +1175,36 @@ int geometry_for(bool fixed, int64_t request_bytes) {
     }
     return g_geom_var_env >= 0 ? g_geom_var_env : kGeomVar;
 }
+// shared-memory-plan variant for a batch of nreq requests (-1: does not fit)
+int geometry_s_for(int64_t nreq) {
+    if (nreq > kPlanSmemMax || nreq > g_plan_smem_default) return -1;
+    if (g_geom_s_env >= 0 && kGeomsS[g_geom_s_env].pcap >= nreq) return g_geom_s_env;
+    return nreq <= 4096 ? 0 : 1;
+}
 
-template <bool FIXED, int NW, int S, int CH>
-int launch_gather_t(const GatherArgs &args, cudaStream_t stream) {
-    constexpr int smem = NW * S * (CH + 32);
+constexpr int smem_bytes_of(int nw, int s, int ch, int pcap) { return nw * s * (ch + 32) + (pcap ? pcap * 12 + 16 : 0); }
+int static_smem_of(int nw, int s) { return nw * s * (8 + 32 * 16) + 16 * 8 + 64; }
+int ctas_per_sm_for(int nw, int s, int ch, int pcap) {
+    int per_sm = g_ctas_per_sm;
+    while (per_sm > 1 && per_sm * (smem_bytes_of(nw, s, ch, pcap) + static_smem_of(nw, s) + 1024) > 227 * 1024) per_sm--;
+    return per_sm;
+}
+
+template <bool FIXED, int NW, int S, int CH, int PCAP>
+int launch_gather_t(const GatherArgs &args_in, cudaStream_t stream) {
+    constexpr int smem = smem_bytes_of(NW, S, CH, PCAP);
     static std::atomic<unsigned long long> configured{0}; // bit d: attribute set on device d (it is per device)
-    auto kern = dds_gather_kernel<FIXED, NW, S, CH>;
+    auto kern = dds_gather_kernel<FIXED, NW, S, CH, PCAP>;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured.load() & (1ull << dev))) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev < 64) configured.fetch_or(1ull << dev);
     }
-    int per_sm = g_ctas_per_sm;
-    while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;
+    const int per_sm = ctas_per_sm_for(NW, S, CH, PCAP);
+    GatherArgs args = args_in;
+    args.dbg = g_dbg;
+    if (g_dbg) CUDA_TRY(cudaMemsetAsync(g_dbg, 0, 1024 * 4 * 8, stream));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(g_sms * per_sm));
     cfg.blockDim = dim3(NW * 32);
@@ -1060,15 +1240,32 @@ int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, A
 
 template <bool FIXED>
 int launch_gather(const GatherArgs &args, cudaStream_t stream) {
-    if (int rc = pick_geometry()) return rc;
     switch (geometry_for(FIXED, FIXED ? args.count * args.var.row_bytes : 0)) {
-    case 1: return launch_gather_t<FIXED, 8, 6, 4096>(args, stream);
-    case 2: return launch_gather_t<FIXED, 16, 3, 4096>(args, stream);
-    case 3: return launch_gather_t<FIXED, 4, 4, 8192>(args, stream);
-    case 4: return launch_gather_t<FIXED, 12, 4, 4096>(args, stream);
-    case 5: return launch_gather_t<FIXED, 4, 6, 4096>(args, stream);
-    default: return launch_gather_t<FIXED, 8, 4, 4096>(args, stream);
+    case 1: return launch_gather_t<FIXED, 8, 6, 4096, 0>(args, stream);
+    case 2: return launch_gather_t<FIXED, 16, 3, 4096, 0>(args, stream);
+    case 3: return launch_gather_t<FIXED, 4, 4, 8192, 0>(args, stream);
+    case 4: return launch_gather_t<FIXED, 12, 4, 4096, 0>(args, stream);
+    case 5: return launch_gather_t<FIXED, 4, 6, 4096, 0>(args, stream);
+    default: return launch_gather_t<FIXED, 8, 4, 4096, 0>(args, stream);
     }
+}
+int launch_gather_s(int g, const GatherArgs &args, cudaStream_t stream) {
+    switch (g) {
+    case 1: return launch_gather_t<false, 12, 3, 3072, 8192>(args, stream);
+    case 2: return launch_gather_t<false, 16, 3, 2048, 8192>(args, stream);
+    case 3: return launch_gather_t<false, 16, 3, 3072, 4096>(args, stream);
+    case 4: return launch_gather_t<false, 8, 4, 4096, 4096>(args, stream);
+    default: return launch_gather_t<false, 12, 3, 4096, 4096>(args, stream);
+    }
+}
+
+void fill_overlap(GatherArgs &a, const ddsk_scratch_t *scr, int flags) {
+    a.overlap = (flags & DDSK_F_OVERLAP) ? 1 : 0;
+    a.skip_wait = (flags & DDSK_F_SKIP_WAIT) ? 1 : 0;
+    a.wait1_valid = (flags & DDSK_F_PREV1) ? 1 : 0;
+    a.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
+    a.seq = scr->ovl_seq;
+    a.ovl = scr->ovl;
 }
 
 } // namespace
@@ -1080,6 +1277,13 @@ extern "C" {
 
 const char *ddsk_last_cuda_error(void) { return g_cuda_err; }
 unsigned long long ddsk_launch_count(void) { return g_launches.load(); }
+int64_t ddsk_plan_smem_max(void) { return kPlanSmemMax; }
+int ddsk_debug_timing(unsigned long long *host_out, int max_ctas) { // [cta][4] of the last gather launch; returns CTAs
+    if (!g_dbg) return 0;
+    const int n = max_ctas < 1024 ? max_ctas : 1024;
+    if (cudaMemcpy(host_out, g_dbg, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
 
 void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes) {
     if (pick_geometry()) {
@@ -1087,22 +1291,20 @@ void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk
         return;
     }
     const Geometry &g = kGeoms[geometry_for(true, 4096)];
-    int smem = g.nw * g.stages * (g.ch + 32);
-    int per_sm = g_ctas_per_sm;
-    while (per_sm > 1 && per_sm * (smem + 2048) > 227 * 1024) per_sm--;
-    *ctas = g_sms * per_sm;
+    *ctas = g_sms * ctas_per_sm_for(g.nw, g.stages, g.ch, 0);
     *warps_per_cta = g.nw;
     *stages = g.stages;
     *chunk_bytes = g.ch;
-    *smem_bytes = smem;
+    *smem_bytes = smem_bytes_of(g.nw, g.stages, g.ch, 0);
 }
 
 int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,
-                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int reset_status,
+                      int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int flags,
                       void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (reset_status & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (flags & DDSK_F_RESET) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0) return 0;
+    if (int rc = pick_geometry()) return rc;
     GatherArgs a;
     memset(&a, 0, sizeof(a));
     a.var = *var;
@@ -1113,107 +1315,95 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
     a.dst_cap = dst_capacity;
     a.offsets_out = offsets_dev_or_null;
     a.status = scr->status;
-    a.overlap = (reset_status & 4) ? 1 : 0;    // bit 2: independent batch -> static segment striding
-    a.skip_wait = (reset_status & 16) ? 1 : 0; // bit 4: ... whose predecessor was one too -> no grid wait
     a.counters = scr->counters;
-    a.host_mirror = reset_status & 2 ? scr->host_mirror : nullptr; // bit 1 of the flags word: mirror wanted
+    a.min_seg_chunks = 1;
+    fill_overlap(a, scr, flags);
+    a.host_mirror = (flags & DDSK_F_MIRROR) ? scr->host_mirror : nullptr;
     return launch_gather<true>(a, st);
 }
 
-int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev, int64_t dst_capacity,
-                    int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int reset_status, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (reset_status & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
-    if (nreq <= 0) return 0;
-    if (nreq > scr->cap_req) {
-        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_var: scratch too small (%lld > %lld)", (long long)nreq,
-                 (long long)scr->cap_req);
+// shared by ddsk_gather_var / ddsk_gather_multi: plan (in the launch, or by the two plan kernels) + gather
+static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq, int64_t cap_total, GatherArgs &a,
+                           int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int flags, cudaStream_t st) {
+    a.nreq = nreq;
+    a.status = scr->status;
+    a.counters = scr->counters;
+    a.host_mirror = (flags & DDSK_F_MIRROR) ? scr->host_mirror : nullptr;
+    a.plan = p; // the gather needs nvars / per_var even when the plan ran in its own kernels
+    a.total_out = scr->total;
+    const int gs = (g_smem_plan && cap_total < ((int64_t)1 << 32)) ? geometry_s_for(nreq) : -1;
+    if (gs >= 0) {
+        a.offsets_out = offsets_dev_or_null;
+        a.min_seg_chunks = g_min_seg_s;
+        fill_overlap(a, scr, flags); // no scratch is shared between launches: independent batches may overlap
+        return launch_gather_s(gs, a, st);
+    }
+    if (nreq > scr->cap_req || cap_total / SEG_GRAIN + 2 > scr->seg_cap) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_var: scratch too small (%lld requests > %lld, or %lld segments > %lld)",
+                 (long long)nreq, (long long)scr->cap_req, (long long)(cap_total / SEG_GRAIN + 2), (long long)scr->seg_cap);
         return -2;
     }
+    // DDS_OVERLAP here means: `scr` carries a scratch slot of this launch's own (slot = ovl_seq & 3), so the plan kernels
+    // may run while the previous batch's gather is still going, and the gather overlaps with its tail.
+    PlanProto pr;
+    memset(&pr, 0, sizeof(pr));
+    if (flags & DDSK_F_OVERLAP) {
+        pr.ovl = scr->ovl;
+        pr.seq = scr->ovl_seq;
+        pr.skip_wait = (flags & DDSK_F_SKIP_WAIT) ? 1 : 0;
+        pr.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
+        pr.wait4_valid = (flags & DDSK_F_PREV4) ? 1 : 0;
+    }
+    const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
+    if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq, scr->req_src,
+                            scr->req_dst, scr->tile_sums, scr->status, pr))
+        return rc;
+    if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
+                            (const int64_t *)scr->tile_sums, offsets_dev_or_null, scr->seg_tab, scr->seg_cap, scr->status, pr))
+        return rc;
+    a.req_src = scr->req_src;
+    a.req_dst = scr->req_dst;
+    a.seg_tab = scr->seg_tab;
+    a.total_out = nullptr;
+    a.min_seg_chunks = g_min_seg_var;
+    fill_overlap(a, scr, flags);
+    a.skip_wait = 0; // the gather always waits for its own plan kernels (which finished long ago in a running queue)
+    return launch_gather<false>(a, st);
+}
+
+int ddsk_var_uses_scratch(int64_t nreq, int64_t dst_capacity) {
+    if (pick_geometry()) return 1;
+    return !(g_smem_plan && dst_capacity < ((int64_t)1 << 32) && geometry_s_for(nreq) >= 0);
+}
+
+int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev, int64_t dst_capacity,
+                    int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int flags, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flags & DDSK_F_RESET) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (nreq <= 0) return 0;
     if (int rc = pick_geometry()) return rc;
     PlanSrc p;
     memset(&p, 0, sizeof(p));
     p.starts = index->starts;
     p.counts = index->counts;
     p.ids = index->sample_ids;
-    p.tab_start = index->table_start;
-    p.tab_count = index->table_count;
+    p.tab = (const longlong2 *)index->table;
     p.nsamples = index->nsamples;
-    // measured (profiles/r1_configs.md): the in-kernel plan wins below ~8K requests (one launch instead of two or
-    // three: B=4096 54 -> 48 us), separate plan kernels are ~2 % faster above (they overlap the previous gather's tail)
-    const bool ovl = (reset_status & 4) != 0; // independent batch in its own scratch slot: always planned in-kernel
-    const bool fused = ovl || (g_fused_plan == 1 ? nreq <= 8192 : g_fused_plan == 2);
-    if (!fused) {
-        // one CTA is enough for explicit (start, count) arrays (coalesced loads); the sample-index lookups are random
-        // two-level gathers and want more SMs' worth of memory parallelism (measured: 1 CTA costs +25 us at B=4096)
-        if (nreq <= (p.ids ? (int64_t)PLAN_TILE : (int64_t)PLAN1_MAX)) {
-            if (int rc = launch_pdl(dds_plan_single_kernel, dim3(1), dim3(PLAN1_THREADS), st, *var, p, nreq, scr->req_src,
-                                    scr->req_dst, offsets_dev_or_null, scr->status))
-                return rc;
-        } else {
-            const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
-            if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq,
-                                    scr->req_src, scr->req_dst, scr->tile_sums, scr->status))
-                return rc;
-            if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
-                                    (const int64_t *)scr->tile_sums, offsets_dev_or_null))
-                return rc;
-        }
-    }
     GatherArgs a;
     memset(&a, 0, sizeof(a));
     a.var = *var;
-    a.req_src = scr->req_src;
-    a.req_dst = scr->req_dst;
-    a.nreq = nreq;
     a.dst = (char *)dst_dev;
     a.dst_cap = dst_capacity;
-    a.status = scr->status;
-    a.counters = scr->counters;
-    a.host_mirror = reset_status & 2 ? scr->host_mirror : nullptr;
-    if (fused) {
-        a.plan = p;
-        a.tile_state = (unsigned long long *)scr->tile_sums;
-        scr->epoch = (scr->epoch + 1) & 0x3FFFFFu;
-        if (scr->epoch == 0) { // 22-bit tag wrapped: clear the words so a stale tag can never look current
-            CUDA_TRY(cudaMemsetAsync(scr->tile_sums, 0, (size_t)(scr->cap_req / 128 + 2) * 8, st));
-            scr->epoch = 1;
-        }
-        a.epoch = scr->epoch;
-        a.fused_plan = 1;
-        a.offsets_out = offsets_dev_or_null;
-    }
-    if (ovl) {
-        a.overlap = 1;
-        a.skip_wait = (reset_status & 16) ? 1 : 0;
-        a.ticket_base = scr->ticket_base;
-        a.tiles_base = scr->tiles_base;
-        a.finish_target = scr->finish_target;
-        const Geometry &g = kGeoms[geometry_for(false, 0)];
-        int per_sm = g_ctas_per_sm;
-        while (per_sm > 1 && per_sm * (g.nw * g.stages * (g.ch + 32) + 2048) > 227 * 1024) per_sm--;
-        const unsigned int nwarps = (unsigned int)(g_sms * per_sm * g.nw);
-        const unsigned int ntiles = (unsigned int)((nreq + TILE_REQ - 1) / TILE_REQ);
-        scr->ticket_base += ntiles + nwarps; // every warp makes exactly one failing ticket claim
-        scr->tiles_base += ntiles;
-        scr->finish_target += nwarps;
-    }
-    return launch_gather<false>(a, st);
+    return plan_and_gather(var, p, nreq, dst_capacity, a, offsets_dev_or_null, scr, flags, st);
 }
 
 int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int64_t nreq, ddsk_scratch_t *scr, int flags,
                       void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (flags & 1) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
+    if (flags & DDSK_F_RESET) CUDA_TRY(cudaMemsetAsync(scr->status, 0xFF, sizeof(unsigned long long), st));
     if (nreq <= 0 || m->nvars <= 0) return 0;
     if (m->nvars > DDSK_MAX_MULTI) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_multi: more than %d variables", DDSK_MAX_MULTI);
-        return -2;
-    }
-    const int64_t total_req = nreq * m->nvars;
-    if (total_req > scr->cap_req) {
-        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_gather_multi: scratch too small (%lld > %lld)", (long long)total_req,
-                 (long long)scr->cap_req);
         return -2;
     }
     if (int rc = pick_geometry()) return rc;
@@ -1223,50 +1413,41 @@ int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int6
     p.nvars = m->nvars;
     p.per_var = nreq;
     p.mvars = m->vars_dev;
+    int64_t cap_total = 0;
     for (int v = 0; v < m->nvars; v++) {
-        p.mtab_start[v] = m->table_start[v];
-        p.mtab_count[v] = m->table_count[v];
+        p.mtab[v] = (const longlong2 *)m->table[v];
         p.mnsamples[v] = m->nsamples[v];
+        cap_total += m->cap[v]; // (saturation is irrelevant: anything >= 4 GiB selects the plan kernels)
+        if (cap_total < 0 || m->cap[v] < 0) cap_total = INT64_MAX / 2;
     }
     ddsk_var_t dummy;
     memset(&dummy, 0, sizeof(dummy));
-    const bool fused = g_fused_plan == 1 ? total_req <= 8192 : g_fused_plan == 2;
-    if (!fused) {
-        const int tiles = (int)((total_req + PLAN_TILE - 1) / PLAN_TILE);
-        if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, dummy, p, total_req,
-                                scr->req_src, scr->req_dst, scr->tile_sums, scr->status))
-            return rc;
-        if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, total_req, scr->req_dst,
-                                (const int64_t *)scr->tile_sums, (int64_t *)nullptr))
-            return rc;
-    }
     GatherArgs a;
     memset(&a, 0, sizeof(a));
-    a.req_src = scr->req_src;
-    a.req_dst = scr->req_dst;
-    a.nreq = total_req;
     a.dst = nullptr;
     a.dst_cap = INT64_MAX;
-    a.status = scr->status;
-    a.counters = scr->counters;
-    a.host_mirror = flags & 2 ? scr->host_mirror : nullptr;
-    a.plan = p; // the gather needs nvars / per_var even when the plan ran in its own kernels
     for (int v = 0; v < m->nvars; v++) {
         a.mdst[v] = (char *)m->dst[v];
         a.mcap[v] = m->cap[v];
         a.moffsets[v] = m->offsets[v];
     }
-    if (fused) {
-        a.tile_state = (unsigned long long *)scr->tile_sums;
-        scr->epoch = (scr->epoch + 1) & 0x3FFFFFu;
-        if (scr->epoch == 0) {
-            CUDA_TRY(cudaMemsetAsync(scr->tile_sums, 0, (size_t)(scr->cap_req / 128 + 2) * 8, st));
-            scr->epoch = 1;
-        }
-        a.epoch = scr->epoch;
-        a.fused_plan = 1;
-    }
-    return launch_gather<false>(a, st);
+    return plan_and_gather(&dummy, p, nreq * m->nvars, cap_total, a, nullptr, scr, flags, st);
+}
+
+int ddsk_small_get(const ddsk_var_t *var, int64_t start, int64_t count, void *dst, int64_t dst_capacity,
+                   unsigned long long *flag_dev, unsigned long long ticket, void *stream) {
+    dds_small_get_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*var, start, count, (char *)dst, dst_capacity, flag_dev, ticket);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ddsk_occupy(int ctas, int smem_bytes, unsigned long long ns, void *stream) {
+    if (ctas <= 0) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(dds_occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    dds_occupy_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(ns);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int64_t disp, int itemsize, uint64_t seed,
@@ -1283,6 +1464,27 @@ int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int
     case 8: dds_synth_kernel<uint64_t><<<blocks, 256, 0, st>>>((uint64_t *)base_dev, first, nelem, seed); break;
     default:
         snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_synth_fill: unsupported itemsize %d", itemsize);
+        return -2;
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ddsk_synth_verify(const ddsk_var_t *var, const void *packed_dev, const int64_t *starts_dev, const int64_t *counts_dev_or_null,
+                      int64_t fixed_count, const int64_t *offsets_dev_or_null, int64_t nreq, int64_t disp, int itemsize,
+                      uint64_t seed, unsigned long long *out_dev, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nreq <= 0) return 0;
+    const int blocks = 148 * 8;
+    const unsigned char *pk = (const unsigned char *)packed_dev;
+    switch (itemsize) {
+    case 1: dds_verify_kernel<uint8_t><<<blocks, 256, 0, st>>>(*var, pk, starts_dev, counts_dev_or_null, fixed_count, offsets_dev_or_null, nreq, disp, seed, out_dev); break;
+    case 2: dds_verify_kernel<uint16_t><<<blocks, 256, 0, st>>>(*var, pk, starts_dev, counts_dev_or_null, fixed_count, offsets_dev_or_null, nreq, disp, seed, out_dev); break;
+    case 4: dds_verify_kernel<uint32_t><<<blocks, 256, 0, st>>>(*var, pk, starts_dev, counts_dev_or_null, fixed_count, offsets_dev_or_null, nreq, disp, seed, out_dev); break;
+    case 8: dds_verify_kernel<uint64_t><<<blocks, 256, 0, st>>>(*var, pk, starts_dev, counts_dev_or_null, fixed_count, offsets_dev_or_null, nreq, disp, seed, out_dev); break;
+    default:
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "ddsk_synth_verify: unsupported itemsize %d", itemsize);
         return -2;
     }
     g_launches++;

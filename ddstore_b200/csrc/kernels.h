@@ -34,53 +34,64 @@ typedef struct ddsk_var {
 
 /* scratch a store owns for the batched path (all device memory) */
 typedef struct ddsk_scratch {
-    unsigned long long *status; /* 1 word */
-    unsigned int *counters;     /* 4 words: [0] segment ticket, [1] finished warps, [2] plan ticket,
-                                   [3] finished plan tiles -- all self-resetting */
+    unsigned long long *status; /* 1 word, sticky (kernels only atomicMin into it) */
+    int64_t *total;             /* 1 word: packed total of the last variable-count launch planned in shared memory */
+    unsigned int *counters;     /* 2 words: [0] segment ticket, [1] finished warps -- self-resetting */
+    unsigned int *ovl;          /* 8 words of the overlap protocol: [0..3] finished-warp counters, [4..7] done words */
+    unsigned int ovl_seq;       /* sequence number the NEXT overlap launch carries (host side, set by the caller) */
+    /* plan in global memory (variable-count batches above ddsk_plan_smem_max() requests, or >= 4 GiB destinations) */
     uint64_t *req_src;          /* [cap_req]   planned source address per request (0 = skip) */
     int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
-    int64_t *tile_sums;         /* [cap_req/128 + 2] tile sums (separate plan kernels) / look-back words (fused plan) */
+    int64_t *tile_sums;         /* [cap_req/1024 + 2] tile sums of the plan kernels */
     int64_t cap_req;
-    unsigned long long *host_mirror; /* device alias of 2 pinned host words: status, packed total (written by the
-                                        last warp of every gather launch); NULL = not used */
-    unsigned int epoch;         /* host-side launch counter tagging the look-back words (22 bits, 0 = never) */
-    /* slots used by overlapped variable-count launches: their counters only ever grow; these are the values they
-     * will have once every launch queued on the slot so far has retired */
-    unsigned int ticket_base, tiles_base, finish_target;
+    uint32_t *seg_tab;          /* [seg_cap] request covering byte k * 16384 of the packed buffer */
+    int64_t seg_cap;
+    unsigned long long *host_mirror; /* device alias of pinned host words: [0] status, [1] packed total (written by the
+                                        last warp of a gather launch that asks for it), [2] ticket of dds_small_get */
 } ddsk_scratch_t;
 
-/* `flags` of both launchers: bit 0 = reset the status word first, bit 1 = have the kernel's last warp mirror status +
- * total into scr->host_mirror (synchronous calls; costs ~2 us at the kernel's end, so async queues skip it);
- * bit 2 = independent batch (static segment striding instead of the ticket counters; for the variable entry `scr` must
- * then be a scratch slot of its own, used with monotonic counters and planned in-kernel), bit 4 = its predecessor in
- * the queue was one too (skip griddepcontrol.wait: the two overlap).
- * Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
+/* `flags` of the launchers */
+#define DDSK_F_RESET 1      /* reset the status word first */
+#define DDSK_F_MIRROR 2     /* the kernel's last warp mirrors status + total into scr->host_mirror (synchronous calls;
+                               costs ~2 us at the kernel's end, so async queues skip it) */
+#define DDSK_F_OVERLAP 4    /* independent batch: static segment striding, overlap protocol (see kernels.cu) */
+#define DDSK_F_SKIP_WAIT 16 /* ... and the launch right before it in the stream was one too: skip griddepcontrol.wait */
+#define DDSK_F_PREV1 32     /* overlap launch ovl_seq-1 belongs to the same run (retire after it) */
+#define DDSK_F_PREV2 64     /* overlap launch ovl_seq-2 belongs to the same run (do not write before it retired) */
+#define DDSK_F_PREV4 128    /* overlap launch ovl_seq-4 belongs to the same run (it used the same plan scratch slot) */
+
+/* Fixed-count batch: every request fetches `count` rows; offsets are i*count*row_bytes.
  * One launch: validate + owner lookup + gather + pack. */
 int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t count, int64_t nreq, void *dst_dev,
                       int64_t dst_capacity, int64_t *offsets_dev_or_null, const ddsk_scratch_t *scr, int flags,
                       void *stream);
 
 /* Where the (start row, row count) of request i comes from (all device pointers): explicit arrays, or -- when
- * sample_ids is set -- the per-sample table of the variable: start = table_start[sample_ids[i]], etc. */
+ * sample_ids is set -- the per-sample table of the variable: {start, count} = table[sample_ids[i]] (int64 pairs). */
 typedef struct ddsk_index {
     const int64_t *starts, *counts;
     const int64_t *sample_ids;
-    const int64_t *table_start, *table_count;
+    const int64_t *table; /* [nsamples][2] */
     int64_t nsamples;
 } ddsk_index_t;
 
-/* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. */
+/* Variable-count batch: plan (lookup + validate + exclusive scan) then gather + pack. The plan runs inside the gather
+ * launch (every CTA for itself, in shared memory) for small batches into < 4 GiB; else in two plan kernels writing the
+ * scratch arrays of `scr` (ddsk_var_uses_scratch tells which). With DDSK_F_OVERLAP the scratch arrays must be a slot
+ * of the launch's own (slot = ovl_seq & 3): the plan then runs under the previous batch's gather. */
 int ddsk_gather_var(const ddsk_var_t *var, const ddsk_index_t *index, int64_t nreq, void *dst_dev,
                     int64_t dst_capacity, int64_t *offsets_dev_or_null, ddsk_scratch_t *scr, int flags,
                     void *stream);
+int ddsk_var_uses_scratch(int64_t nreq, int64_t dst_capacity);
+int64_t ddsk_plan_smem_max(void);
 
 /* Multi-array batch: the rows of the SAME nreq sample ids in nvars (<= DDSK_MAX_MULTI) variables, one launch. vars_dev =
- * device array of the variables' windows; table_*[v] = sample index of variable v; dst[v]/cap[v]/offsets[v] per variable
- * (offsets[v] nullable, nreq+1 entries). On return of the stream, totals are req_dst-derived (see store.cpp). */
+ * device array of the variables' windows; table[v] = sample index of variable v; dst[v]/cap[v]/offsets[v] per variable
+ * (offsets[v] nullable, nreq+1 entries). */
 typedef struct ddsk_multi {
     int nvars;
     const ddsk_var_t *vars_dev;
-    const int64_t *table_start[DDSK_MAX_MULTI], *table_count[DDSK_MAX_MULTI];
+    const int64_t *table[DDSK_MAX_MULTI]; /* [nsamples[v]][2] */
     int64_t nsamples[DDSK_MAX_MULTI];
     void *dst[DDSK_MAX_MULTI];
     int64_t cap[DDSK_MAX_MULTI];
@@ -89,10 +100,28 @@ typedef struct ddsk_multi {
 int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int64_t nreq, ddsk_scratch_t *scr, int flags,
                       void *stream);
 
+/* One request in a 1-CTA kernel (the legacy per-sample get()): checks + copy into `dst` (device memory or mapped pinned
+ * host memory), then flag[0] = status word, flag[1] = bytes, flag[2] = ticket (flag = mapped pinned host words). */
+int ddsk_small_get(const ddsk_var_t *var, int64_t start, int64_t count, void *dst, int64_t dst_capacity,
+                   unsigned long long *flag_dev, unsigned long long ticket, void *stream);
+
 /* Synthetic payload: element (global_row g, col c) = low itemsize bytes of
  * splitmix64(seed ^ (g*disp + c)). Bench / test helper, fills a local shard in place. */
 int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int64_t disp, int itemsize, uint64_t seed,
                     void *stream);
+
+/* Check a packed batch against the generator on the device: request i = rows [starts[i], +counts[i] or fixed_count) at
+ * byte offset offsets[i] (or i * fixed_count * disp * itemsize). out_dev: 2 + DDSK_MAX_RANKS words, accumulated into:
+ * [0] mismatching elements, [1] rows checked, [2 + r] requests owned by rank r. */
+int ddsk_synth_verify(const ddsk_var_t *var, const void *packed_dev, const int64_t *starts_dev,
+                      const int64_t *counts_dev_or_null, int64_t fixed_count, const int64_t *offsets_dev_or_null,
+                      int64_t nreq, int64_t disp, int itemsize, uint64_t seed, unsigned long long *out_dev, void *stream);
+
+/* test helper: `ctas` CTAs holding `smem_bytes` of shared memory each for `ns` nanoseconds on `stream` */
+int ddsk_occupy(int ctas, int smem_bytes, unsigned long long ns, void *stream);
+
+/* DDS_DEBUG_TIMING=1: per-CTA globaltimer stamps [entry, plan done, first data, last warp done] of the last gather launch */
+int ddsk_debug_timing(unsigned long long *host_out, int max_ctas);
 
 /* launch geometry actually used (for bench reporting / DESIGN.md) */
 void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes);

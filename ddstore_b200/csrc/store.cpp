@@ -12,14 +12,17 @@
 // All CUDA work goes through the CUDA runtime C API and the ddsk_* launchers (kernels.h).
 // There is no CPU data path: if no device is usable, dds_create fails with DDS_ERR_NO_DEVICE.
 #include <cuda_runtime_api.h>
+#include <sys/random.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -98,7 +101,7 @@ struct PeerRec { // what every rank publishes in add()/init(): the reference's A
     uint64_t host_tag;
     uint64_t alloc_bytes; // mapped size of the shard block
     int32_t vmm;          // 1: CUDA VMM block shared by POSIX fd; 0: cudaMalloc + legacy cudaIpc handle
-    int32_t pad_;
+    int32_t ok;           // 0: this rank failed locally (bad argument, allocation, fill): every rank fails the call
     cudaIpcMemHandle_t handle;
 };
 
@@ -114,11 +117,13 @@ struct Var {
     dds_vmm::Block block;           // valid when vmm
     std::vector<void *> peer_base;  // as mapped here
     std::vector<char> peer_opened;  // 1 = cudaIpcOpenMemHandle'd (must be closed), 2 = VMM import (peer_block)
+    bool unprotected_peers = false; // a peer reads this shard through a raw pointer / legacy IPC mapping: the memory
+                                    // must not go away before that peer is done (VMM imports hold their own reference)
     std::vector<dds_vmm::Block> peer_block;
     bool fence_active = false;
     ddsk_var_t kv;
     // per-sample index: sample i owns rows [tab_start[i], tab_start[i] + tab_count[i])
-    int64_t *d_tab_start = nullptr, *d_tab_count = nullptr;
+    int64_t *d_tab = nullptr; // [nsamples][2] = {row_start, row_count}: one 16-byte load per sample id
     int64_t nsamples = 0;
     std::vector<int64_t> h_tab_count;
 };
@@ -149,15 +154,25 @@ struct dds_store {
     cudaStream_t pending_stream = nullptr;
     int64_t pending_fixed_total = -1;
     int64_t pending_nreq = 0;
-    // scratch slots of overlapped variable-count batches (DDS_OVERLAP): each launch plans into its own slot
-    static constexpr int kRing = 4;
-    ddsk_scratch_t ring[kRing];
-    int ring_next = 0;
     const int64_t *pending_total_ptr = nullptr; // device word holding the packed total of the last queued launch
     ddsk_var_t *d_multi_vars = nullptr; // device copy of the windows of the last multi-array combination
     std::string multi_key;
-    bool prev_fixed = false;
-    bool prev_overlap = false; // the previous launch was a DDS_OVERLAP batch (then the next one may skip the grid wait)
+    // overlap protocol (DDS_OVERLAP): sequence number of the next overlap launch, and how many overlap launches in a
+    // row were chained on the pending stream right before it (0: the next one starts a new run)
+    unsigned int ovl_seq = 1;
+    int run_len = 0;
+    // plan scratch slots of overlapped variable-count batches: launch q plans into slot q & 3, so its plan kernels can
+    // run while the gather of launch q-1 is still reading slot (q-1) & 3
+    struct Slot {
+        uint64_t *req_src = nullptr;
+        int64_t *req_dst = nullptr, *tile_sums = nullptr;
+        uint32_t *seg_tab = nullptr;
+        int64_t cap_req = 0, seg_cap = 0;
+    } slots[4];
+    int64_t *d_offs = nullptr; // device staging of byte offsets (host destinations, multi-array totals)
+    int64_t offs_cap = 0;
+    unsigned long long small_ticket = 0; // ticket of the last dds_small_get launch
+    std::set<cudaStream_t> update_streams; // caller streams that carried dds_update_async copies since the last fence
 };
 
 namespace {
@@ -170,48 +185,88 @@ uint64_t host_tag() {
     return h;
 }
 
-int ensure_scratch(dds_store *s, int64_t nreq) {
-    if (nreq <= s->scr.cap_req) return DDS_OK;
-    int64_t cap = std::max<int64_t>(4096, s->scr.cap_req);
-    while (cap < nreq) cap *= 2;
-    if (s->scr.req_src) cudaFree(s->scr.req_src);
-    if (s->scr.req_dst) cudaFree(s->scr.req_dst);
-    if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
-    s->scr.req_src = nullptr;
-    s->scr.req_dst = nullptr;
-    s->scr.tile_sums = nullptr;
-    s->scr.cap_req = 0;
-    CU(cudaMalloc((void **)&s->scr.req_src, (size_t)cap * 8));
-    CU(cudaMalloc((void **)&s->scr.req_dst, (size_t)(cap + 1) * 8));
-    CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 128 + 2) * 8));
-    CU(cudaMemset(s->scr.tile_sums, 0, (size_t)(cap / 128 + 2) * 8));
-    s->scr.cap_req = cap;
+// scratch of the plan kernels (variable-count batches the shared-memory plan does not take)
+int ensure_scratch(dds_store *s, int64_t nreq, int64_t cap_bytes) {
+    if (nreq > s->scr.cap_req) {
+        int64_t cap = std::max<int64_t>(16384, s->scr.cap_req);
+        while (cap < nreq) cap *= 2;
+        CU(cudaDeviceSynchronize()); // nothing queued may still be reading the old arrays
+        if (s->scr.req_src) cudaFree(s->scr.req_src);
+        if (s->scr.req_dst) cudaFree(s->scr.req_dst);
+        if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
+        s->scr.req_src = nullptr;
+        s->scr.req_dst = nullptr;
+        s->scr.tile_sums = nullptr;
+        s->scr.cap_req = 0;
+        CU(cudaMalloc((void **)&s->scr.req_src, (size_t)cap * 8));
+        CU(cudaMalloc((void **)&s->scr.req_dst, (size_t)(cap + 1) * 8));
+        CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+        s->scr.cap_req = cap;
+    }
+    const int64_t need = cap_bytes / 16384 + 2; // one entry per SEG_GRAIN of the packed buffer
+    if (need > s->scr.seg_cap) {
+        int64_t cap = std::max<int64_t>(1 << 16, s->scr.seg_cap);
+        while (cap < need) cap *= 2;
+        CU(cudaDeviceSynchronize());
+        if (s->scr.seg_tab) cudaFree(s->scr.seg_tab);
+        s->scr.seg_tab = nullptr;
+        s->scr.seg_cap = 0;
+        CU(cudaMalloc((void **)&s->scr.seg_tab, (size_t)cap * 4));
+        s->scr.seg_cap = cap;
+    }
     return DDS_OK;
 }
 
-int ensure_ring(dds_store *s, int64_t nreq, cudaStream_t st) {
-    if (s->ring[0].cap_req >= nreq) return DDS_OK;
-    int64_t cap = std::max<int64_t>(8192, s->ring[0].cap_req);
+int ensure_slots(dds_store *s, int64_t nreq, int64_t cap_bytes) {
+    const int64_t need_seg = cap_bytes / 16384 + 2;
+    if (nreq <= s->slots[0].cap_req && need_seg <= s->slots[0].seg_cap) return DDS_OK;
+    int64_t cap = std::max<int64_t>(16384, s->slots[0].cap_req), scap = std::max<int64_t>(1 << 16, s->slots[0].seg_cap);
     while (cap < nreq) cap *= 2;
-    CU(cudaStreamSynchronize(st)); // nothing queued may still be using the old slots
-    CU(cudaDeviceSynchronize());
-    for (int k = 0; k < dds_store::kRing; k++) {
-        ddsk_scratch_t &r = s->ring[k];
-        if (r.req_src) cudaFree(r.req_src);
-        if (r.req_dst) cudaFree(r.req_dst);
-        if (r.tile_sums) cudaFree(r.tile_sums);
-        if (r.counters) cudaFree(r.counters);
-        memset(&r, 0, sizeof(r));
-        CU(cudaMalloc((void **)&r.req_src, (size_t)cap * 8));
-        CU(cudaMalloc((void **)&r.req_dst, (size_t)(cap + 1) * 8));
-        CU(cudaMalloc((void **)&r.tile_sums, (size_t)(cap / 128 + 2) * 8));
-        CU(cudaMemset(r.tile_sums, 0, (size_t)(cap / 128 + 2) * 8));
-        CU(cudaMalloc((void **)&r.counters, 16));
-        CU(cudaMemset(r.counters, 0, 16));
-        r.status = s->scr.status; // one sticky status word per store
-        r.host_mirror = nullptr;
-        r.cap_req = cap;
+    while (scap < need_seg) scap *= 2;
+    CU(cudaDeviceSynchronize()); // nothing queued may still be using the old slots
+    s->run_len = 0;              // ... so the next overlap launch starts a new run
+    for (auto &sl : s->slots) {
+        if (sl.req_src) cudaFree(sl.req_src);
+        if (sl.req_dst) cudaFree(sl.req_dst);
+        if (sl.tile_sums) cudaFree(sl.tile_sums);
+        if (sl.seg_tab) cudaFree(sl.seg_tab);
+        sl = dds_store::Slot();
+        CU(cudaMalloc((void **)&sl.req_src, (size_t)cap * 8));
+        CU(cudaMalloc((void **)&sl.req_dst, (size_t)(cap + 1) * 8));
+        CU(cudaMalloc((void **)&sl.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+        CU(cudaMalloc((void **)&sl.seg_tab, (size_t)scap * 4));
+        sl.cap_req = cap;
+        sl.seg_cap = scap;
     }
+    return DDS_OK;
+}
+
+// the scratch a launch works in: the store's own arrays, or -- for an overlap launch planned by the plan kernels --
+// slot (sequence number & 3)
+ddsk_scratch_t scratch_view(dds_store *s, bool slot) {
+    ddsk_scratch_t v = s->scr;
+    if (slot) {
+        const dds_store::Slot &sl = s->slots[s->scr.ovl_seq & 3u];
+        v.req_src = sl.req_src;
+        v.req_dst = sl.req_dst;
+        v.tile_sums = sl.tile_sums;
+        v.seg_tab = sl.seg_tab;
+        v.cap_req = sl.cap_req;
+        v.seg_cap = sl.seg_cap;
+    }
+    return v;
+}
+
+int ensure_offs(dds_store *s, int64_t n) {
+    if (n <= s->offs_cap) return DDS_OK;
+    int64_t cap = std::max<int64_t>(4096, s->offs_cap);
+    while (cap < n) cap *= 2;
+    CU(cudaDeviceSynchronize());
+    if (s->d_offs) cudaFree(s->d_offs);
+    s->d_offs = nullptr;
+    s->offs_cap = 0;
+    CU(cudaMalloc((void **)&s->d_offs, (size_t)cap * 8));
+    s->offs_cap = cap;
     return DDS_OK;
 }
 
@@ -259,9 +314,8 @@ void release_var(Var &v, int rank) {
 }
 
 void free_shard(Var &v) {
-    if (v.d_tab_start) cudaFree(v.d_tab_start);
-    if (v.d_tab_count) cudaFree(v.d_tab_count);
-    v.d_tab_start = v.d_tab_count = nullptr;
+    if (v.d_tab) cudaFree(v.d_tab);
+    v.d_tab = nullptr;
     if (v.vmm)
         dds_vmm::release(&v.block);
     else if (v.base)
@@ -269,44 +323,67 @@ void free_shard(Var &v) {
     v.base = nullptr;
 }
 
-// add() and init() share everything but the fill (ddstore.hpp:39-108 vs :110-179)
+// add() and init() share everything but the fill (ddstore.hpp:39-108 vs :110-179).
+// COLLECTIVE: every rank always runs the all-gather, the descriptor exchange (when any is due) and the barrier, in the
+// same order, whatever failed locally -- a local failure (bad argument, out of memory, a failed copy) travels in the
+// all-gathered record (PeerRec.ok) and makes EVERY rank fail consistently afterwards, instead of leaving the peers
+// stuck in a collective the failing rank never entered.
 int register_var(dds_store *s, const char *name, const void *buffer, int64_t nrows, int disp, int itemsize,
                  int buffer_on_device, bool zero_fill) {
     if (!s || !name) return fail(DDS_ERR_ARG, "null store or name");
-    if (nrows < 0 || disp < 0 || itemsize <= 0) return fail(DDS_ERR_ARG, "negative nrows/disp or itemsize <= 0");
-    if (s->size > DDSK_MAX_RANKS) return fail(DDS_ERR_ARG, "communicator larger than DDSK_MAX_RANKS");
-    if (!zero_fill && !buffer && nrows * (int64_t)disp > 0) return fail(DDS_ERR_ARG, "null buffer");
-    CU(cudaSetDevice(s->device));
+    int local_rc = DDS_OK;
+    std::string local_err;
+    auto note = [&](int rc) {
+        if (rc && !local_rc) {
+            local_rc = rc;
+            local_err = dds_last_error();
+        }
+    };
+    auto note_cuda = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess) note(cuda_fail(e, what));
+    };
+    if (nrows < 0 || disp < 0 || itemsize <= 0) note(fail(DDS_ERR_ARG, "negative nrows/disp or itemsize <= 0"));
+    if (s->size > DDSK_MAX_RANKS) note(fail(DDS_ERR_ARG, "communicator larger than DDSK_MAX_RANKS"));
+    if (!zero_fill && !buffer && nrows * (int64_t)disp > 0) note(fail(DDS_ERR_ARG, "null buffer"));
+    note_cuda(cudaSetDevice(s->device), "cudaSetDevice");
     const bool exists = s->vars.count(name) != 0;
     const unsigned long long seq = s->reg_seq++;
 
     // shard: payload + 16 bytes of slack so the kernel's 16-byte-aligned superset loads never leave it
-    const size_t payload = (size_t)nrows * (size_t)disp * (size_t)itemsize;
+    const size_t payload = local_rc ? 0 : (size_t)nrows * (size_t)disp * (size_t)itemsize;
     size_t alloc = ((payload + 16 + 255) / 256) * 256;
     Var v;
     v.vmm = dds_vmm::available(s->device);
     void *base = nullptr;
-    if (v.vmm) {
-        if (int rc = dds_vmm::alloc(s->device, alloc, &v.block)) return rc;
-        base = v.block.ptr;
-        alloc = v.block.size;
-    } else {
-        CU(cudaMalloc(&base, alloc));
+    if (!local_rc) {
+        if (v.vmm) {
+            note(dds_vmm::alloc(s->device, alloc, &v.block));
+            if (!local_rc) {
+                base = v.block.ptr;
+                alloc = v.block.size;
+            }
+        } else {
+            note_cuda(cudaMalloc(&base, alloc), "cudaMalloc (shard)");
+            if (local_rc) base = nullptr;
+        }
     }
     v.base = base;
     v.bytes = alloc;
-    if (zero_fill || payload == 0) {
-        CU(cudaMemsetAsync(base, 0, alloc, s->stream));
-    } else {
-        CU(cudaMemsetAsync((char *)base + payload, 0, alloc - payload, s->stream));
-        CU(cudaMemcpyAsync(base, buffer, payload, buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                           s->stream));
+    if (base) {
+        if (zero_fill || payload == 0) {
+            note_cuda(cudaMemsetAsync(base, 0, alloc, s->stream), "cudaMemsetAsync (shard)");
+        } else {
+            note_cuda(cudaMemsetAsync((char *)base + payload, 0, alloc - payload, s->stream), "cudaMemsetAsync (slack)");
+            note_cuda(cudaMemcpyAsync(base, buffer, payload,
+                                      buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream),
+                      "cudaMemcpyAsync (shard fill)");
+        }
+        note_cuda(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize (shard fill)");
     }
-    CU(cudaStreamSynchronize(s->stream));
 
     PeerRec mine;
     memset(&mine, 0, sizeof(mine));
-    mine.nrows = nrows;
+    mine.nrows = local_rc ? 0 : nrows;
     mine.disp = disp;
     mine.itemsize = itemsize;
     mine.pid = (int32_t)getpid();
@@ -315,32 +392,44 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     mine.host_tag = host_tag();
     mine.alloc_bytes = alloc;
     mine.vmm = v.vmm ? 1 : 0;
-    if (s->size > 1 && !v.vmm) CU(cudaIpcGetMemHandle(&mine.handle, base));
+    if (s->size > 1 && !v.vmm && base) note_cuda(cudaIpcGetMemHandle(&mine.handle, base), "cudaIpcGetMemHandle");
+    mine.ok = local_rc ? 0 : 1;
     std::vector<PeerRec> all((size_t)s->size);
     if (int rc = dds_comm_allgather(s->comm, &mine, all.data(), sizeof(PeerRec))) {
-        free_shard(v);
+        free_shard(v); // the communicator itself is broken: nothing collective can follow
         return rc;
     }
 
     // ddstore.hpp:78-82: every rank must pass the same disp; the ranks that differ from the max throw
     int max_disp = 0;
-    bool bad_item = false, mixed = false, other_host = false, other_proc = false;
+    bool bad_item = false, mixed = false, other_host = false, other_proc = false, peer_failed = false;
     for (auto &p : all) {
         max_disp = std::max(max_disp, (int)p.disp);
         bad_item |= p.itemsize != itemsize;
         mixed |= p.vmm != mine.vmm;
         other_host |= p.host_tag != mine.host_tag;
         other_proc |= p.pid != mine.pid;
+        peer_failed |= !p.ok;
     }
     const bool bad_disp = max_disp != disp;
     int map_rc = DDS_OK;
-    if (mixed) map_rc = fail(DDS_ERR_CUDA, "ranks disagree on the shard allocation mode (set DDS_SHARD_ALLOC on all ranks)");
-    if (other_host)
+    if (peer_failed) {
+        if (local_rc) {
+            g_err = local_err;
+            map_rc = local_rc;
+        } else {
+            map_rc = fail(DDS_ERR_COMM, "a peer rank failed to allocate or fill its shard");
+        }
+    }
+    if (!map_rc && mixed)
+        map_rc = fail(DDS_ERR_CUDA, "ranks disagree on the shard allocation mode (set DDS_SHARD_ALLOC on all ranks)");
+    if (!map_rc && other_host)
         map_rc = fail(DDS_ERR_COMM, "ranks on different hosts: the store spans one NVSwitch box (use one store per box)");
 
-    // ---- build the "window": every rank's shard mapped here. Done on ALL ranks whatever their own verdict, so
-    // the collective steps stay in lock-step (a rank that will fail below still serves its shard to the others,
-    // like the reference's ranks that pass the disp check keep a window containing every rank's buffer).
+    // ---- build the "window": every rank's shard mapped here. Done on ALL ranks whatever their own verdict on
+    // disp / itemsize, so the collective steps stay in lock-step (a rank that will fail below still serves its shard to
+    // the others, like the reference's ranks that pass the disp check keep a window containing every rank's buffer).
+    // Whether the descriptor exchange runs depends only on all-gathered facts, so every rank decides the same.
     v.name = name;
     v.itemsize = itemsize;
     v.disp = disp;
@@ -357,13 +446,16 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     std::vector<int> fds;
     if (!map_rc && v.vmm && other_proc) {
         std::vector<char> want((size_t)s->size, 0);
-        for (int r = 0; r < s->size; r++) want[(size_t)r] = all[(size_t)r].pid != mine.pid;
+        std::vector<int> pids((size_t)s->size, 0);
+        for (int r = 0; r < s->size; r++) {
+            want[(size_t)r] = all[(size_t)r].pid != mine.pid;
+            pids[(size_t)r] = all[(size_t)r].pid;
+        }
         map_rc = dds_vmm::export_fd(&v.block);
         char tag[96];
         snprintf(tag, sizeof(tag), "dds-b200-%016llx-%llu", s->token, seq);
-        // collective even if the export failed (my_fd = -1 would break sendmsg, so send a harmless dup of stdin)
-        int my_fd = v.block.fd >= 0 ? v.block.fd : 0;
-        int xrc = dds_vmm::exchange_fds(s->comm, tag, my_fd, want, &fds);
+        // collective even if the export failed: the message then says "no descriptor"
+        int xrc = dds_vmm::exchange_fds(s->comm, tag, v.block.fd, want, pids, &fds);
         if (!map_rc) map_rc = xrc;
         if (v.block.fd >= 0) { // every peer holds its own duplicate now; one descriptor per variable would add up
             close(v.block.fd);
@@ -376,14 +468,19 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
             v.peer_base[(size_t)r] = base;
         } else if (p.pid == mine.pid) {
             // thread-ranks of one process: the raw pointer is already valid here
+            v.unprotected_peers = true;
             if (p.device != s->device && !v.vmm) {
                 int can = 0;
-                CU(cudaDeviceCanAccessPeer(&can, s->device, p.device));
+                cudaError_t e = cudaDeviceCanAccessPeer(&can, s->device, p.device);
+                if (e != cudaSuccess) {
+                    map_rc = cuda_fail(e, "cudaDeviceCanAccessPeer");
+                    break;
+                }
                 if (!can) {
                     map_rc = fail(DDS_ERR_CUDA, "peer GPUs of one process cannot access each other");
                     break;
                 }
-                cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+                e = cudaDeviceEnablePeerAccess(p.device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
                     map_rc = cuda_fail(e, "cudaDeviceEnablePeerAccess");
                     break;
@@ -404,6 +501,7 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
             v.peer_base[(size_t)r] = v.peer_block[(size_t)r].ptr;
             v.peer_opened[(size_t)r] = 2;
         } else {
+            v.unprotected_peers = true;
             void *mapped = nullptr;
             cudaError_t e = cudaIpcOpenMemHandle(&mapped, p.handle, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
@@ -423,20 +521,28 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
             if (r != s->rank && p.pid == mine.pid && p.device != s->device) map_rc = dds_vmm::grant(&v.block, p.device);
         }
     }
-    std::string keep_err = dds_last_error();
+    const std::string keep_err = dds_last_error(); // (the text of whatever set map_rc)
     int brc = dds_comm_barrier(s->comm); // every shard is filled, mapped and granted before anyone may read it
 
     if (map_rc || bad_disp || bad_item || exists) {
         release_var(v, s->rank);
-        if (v.vmm)
-            s->zombie_blocks.push_back(v.block); // peers may have mapped it; released in dds_free
-        else
-            s->zombies.push_back(base);
+        if (base) {
+            if (v.vmm)
+                s->zombie_blocks.push_back(v.block); // peers may have mapped it; released in dds_free
+            else
+                s->zombies.push_back(base);
+        }
+        if (local_rc) {
+            g_err = local_err;
+            return local_rc;
+        }
+        if (map_rc) {
+            g_err = keep_err;
+            return map_rc;
+        }
         if (bad_disp) return fail(DDS_ERR_DISP);
         if (bad_item) return fail(DDS_ERR_DTYPE);
-        if (exists) return fail(DDS_ERR_EXISTS, name);
-        g_err = keep_err;
-        return map_rc;
+        return fail(DDS_ERR_EXISTS, name);
     }
     memset(&v.kv, 0, sizeof(v.kv));
     for (int r = 0; r < s->size; r++) {
@@ -550,7 +656,6 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
     }
     dds_store *s = new dds_store;
     memset(&s->scr, 0, sizeof(s->scr));
-    memset(s->ring, 0, sizeof(s->ring));
     s->comm = comm;
     s->rank = dds_comm_rank(comm);
     s->size = dds_comm_size(comm);
@@ -558,14 +663,19 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
     s->method = method;
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMalloc((void **)&s->scr.status, 8) == cudaSuccess &&
-              cudaMalloc((void **)&s->scr.counters, 16) == cudaSuccess &&
-              cudaMemset(s->scr.counters, 0, 16) == cudaSuccess &&
+              cudaMalloc((void **)&s->scr.status, 16) == cudaSuccess && // [0] sticky status, [1] packed total
+              cudaMalloc((void **)&s->scr.counters, 64) == cudaSuccess && // 2 ticket words + 8 overlap-protocol words
+              cudaMemset(s->scr.counters, 0, 64) == cudaSuccess &&
               cudaMemset(s->scr.status, 0xFF, 8) == cudaSuccess &&
-              cudaHostAlloc((void **)&s->h_status, 16, cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostAlloc((void **)&s->h_status, 32, cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void **)&s->scr.host_mirror, s->h_status, 0) == cudaSuccess &&
               cudaHostAlloc((void **)&s->h_small, (size_t)(kSmallIdx * 16 + kSmallOut), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void **)&s->d_small, s->h_small, 0) == cudaSuccess;
+    if (ok) {
+        s->scr.total = (int64_t *)(s->scr.status + 1);
+        s->scr.ovl = s->scr.counters + 8;
+        memset(s->h_status, 0, 32);
+    }
     if (!ok) {
         cuda_fail(cudaGetLastError(), "dds_create: device setup");
         delete s;
@@ -573,8 +683,10 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
     }
     // job-unique token (rank 0's) naming the descriptor-passing sockets of this store
     {
-        unsigned long long mine = ((unsigned long long)getpid() << 32) ^ (unsigned long long)(uintptr_t)s ^
-                                  (unsigned long long)time(nullptr) * 0x9E3779B97F4A7C15ull;
+        unsigned long long mine = 0; // unguessable: it names the abstract sockets the shard descriptors travel over
+        if (getrandom(&mine, sizeof(mine), 0) != (ssize_t)sizeof(mine))
+            mine = ((unsigned long long)getpid() << 32) ^ (unsigned long long)(uintptr_t)s ^
+                   (unsigned long long)time(nullptr) * 0x9E3779B97F4A7C15ull;
         std::vector<unsigned long long> all((size_t)s->size);
         if (dds_comm_allgather(comm, &mine, all.data(), sizeof(mine)) != DDS_OK) {
             dds_destroy(s);
@@ -614,6 +726,7 @@ static int update_impl(dds_store_t *s, const char *name, const void *buffer, int
         CU(cudaMemcpyAsync((char *)v->base + (size_t)offset * row, buffer, (size_t)nrows * row,
                            buffer_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         if (sync) CU(cudaStreamSynchronize(st));
+        else if (st != s->stream) s->update_streams.insert(st); // the next fence / free waits for it
     }
     return DDS_OK;
 }
@@ -629,7 +742,68 @@ int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64
                        cuda_stream ? (cudaStream_t)cuda_stream : (s ? s->stream : nullptr), false);
 }
 
+// every copy queued by dds_update_async on a caller's stream has landed (the fences promise the shard is complete)
+static int drain_update_streams(dds_store_t *s) {
+    for (cudaStream_t st : s->update_streams) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            s->update_streams.clear();
+            return cuda_fail(e, "cudaStreamSynchronize (update stream)");
+        }
+    }
+    s->update_streams.clear();
+    return DDS_OK;
+}
+
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);
+
+// flags of an overlap launch (DDS_OVERLAP), and the bookkeeping of the run it belongs to. `chain`: the launch goes on
+// the stream the previous async launch went on, with nothing synchronised in between.
+static int overlap_flags(dds_store_t *s, bool ovl, bool chain) {
+    if (!ovl) {
+        s->run_len = 0;
+        return 0;
+    }
+    if (!chain) s->run_len = 0;
+    int f = DDSK_F_OVERLAP;
+    if (s->run_len >= 1) f |= DDSK_F_SKIP_WAIT | DDSK_F_PREV1;
+    if (s->run_len >= 2) f |= DDSK_F_PREV2;
+    if (s->run_len >= 4) f |= DDSK_F_PREV4;
+    s->scr.ovl_seq = s->ovl_seq++;
+    s->run_len++;
+    return f;
+}
+
+// One request through the 1-CTA kernel: the legacy one-get()-per-sample call. One launch, no stream synchronize: the
+// kernel's last store is a ticket in mapped pinned memory the host spins on.
+static int small_get(dds_store_t *s, Var *v, int64_t start, int64_t count, void *dst, int64_t cap, bool dst_dev,
+                     int64_t *total_bytes, int64_t *bad_index) {
+    cudaStream_t st = s->stream;
+    volatile unsigned long long *flag = s->h_status;
+    const unsigned long long ticket = ++s->small_ticket;
+    void *d_dst = dst_dev ? dst : (void *)(s->d_small + kSmallIdx * 16);
+    if (ddsk_small_get(&v->kv, start, count, d_dst, cap, s->scr.host_mirror, ticket, st))
+        return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    // spin on the ticket (a few microseconds); fall back to a stream synchronize if the kernel died
+    for (unsigned spins = 0; flag[2] != ticket; spins++) {
+        if ((spins & 0x3FFF) == 0x3FFF) {
+            cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaErrorNotReady) {
+                if (q != cudaSuccess) return cuda_fail(q, "dds_small_get_kernel");
+                if (flag[2] != ticket) return fail(DDS_ERR_CUDA, "small get: the kernel finished without publishing its ticket");
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const unsigned long long stw = flag[0];
+    const int64_t n = (int64_t)flag[1];
+    if (!dst_dev && stw == DDSK_STATUS_OK && n > 0) memcpy(dst, s->h_small + kSmallIdx * 16, (size_t)n);
+    if (total_bytes) *total_bytes = n;
+    return decode_status_word(stw, bad_index);
+}
 
 // The one batched path behind dds_get_batch / dds_get_samples / dds_get.
 //   by_sample == false: request i = (starts[i], counts ? counts[i] : fixed_count)
@@ -663,6 +837,14 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
         return DDS_OK;
     }
 
+    // ---- the legacy per-sample call: one request, host indices, synchronous, small result -> 1-CTA kernel
+    if (fixed && nreq == 1 && !idx_dev && !no_sync && !cuda_stream && !dst_offsets) {
+        const int64_t need = fixed_count > 0 ? fixed_count * R : 0;
+        if (need <= (dst_dev ? (int64_t)(1 << 20) : kSmallOut) && (dst || need == 0))
+            return small_get(s, v, starts[0], fixed_count, dst, dst_dev ? dst_capacity : std::min(dst_capacity, kSmallOut), dst_dev,
+                             total_bytes, bad_index);
+    }
+
     // ---- indices to the device (8-16 B per request)
     const int64_t *d_starts = starts, *d_counts = counts;
     if (!idx_dev && nreq <= kSmallIdx) {
@@ -682,9 +864,6 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             CU(cudaMemcpyAsync(s->d_counts, counts, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
             d_counts = s->d_counts;
         }
-    }
-    if (!fixed) {
-        if (int rc = ensure_scratch(s, nreq)) return rc;
     }
 
     // ---- packed size as far as the host can know it
@@ -720,49 +899,42 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
         cap = need;
     }
     if (!d_dst && cap > 0) return fail(DDS_ERR_ARG, "null destination");
+    // DDS_OVERLAP: declared independent of the batch queued right before it (see the protocol in kernels.cu)
+    const bool ovl = no_sync && (flags & DDS_OVERLAP);
+    const bool uses_scratch = !fixed && ddsk_var_uses_scratch(nreq, cap);
+    if (uses_scratch) {
+        if (int rc = ovl ? ensure_slots(s, nreq, cap) : ensure_scratch(s, nreq, cap)) return rc;
+    }
 
     // ---- launch
     int64_t *d_offsets = dst_dev ? dst_offsets : nullptr;
+    if (!dst_dev && dst_offsets && !fixed) { // byte offsets for a host caller: staged on the device, copied back below
+        if (int rc = ensure_offs(s, nreq + 1)) return rc;
+        d_offsets = s->d_offs;
+    }
+    const int kflags = (no_sync ? 0 : DDSK_F_MIRROR) | overlap_flags(s, ovl, chain);
+    ddsk_scratch_t scr = scratch_view(s, uses_scratch && ovl);
     int krc;
     if (fixed) {
-        // DDS_OVERLAP: declared independent of its neighbours in the queue. It never touches the ticket counters;
-        // it also skips the grid wait when the launch right before it (same stream) was one too.
-        const bool ovl = no_sync && (flags & DDS_OVERLAP);
-        const bool skip = ovl && chain && s->prev_overlap;
-        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &s->scr,
-                                (no_sync ? 0 : 2) | (ovl ? 4 : 0) | (skip ? 16 : 0), st);
-        s->prev_overlap = ovl;
+        krc = ddsk_gather_fixed(&v->kv, d_starts, fixed_count, nreq, d_dst, cap, d_offsets, &scr, kflags, st);
     } else {
         ddsk_index_t ix;
         memset(&ix, 0, sizeof(ix));
         if (by_sample) {
             ix.sample_ids = d_starts;
-            ix.table_start = v->d_tab_start;
-            ix.table_count = v->d_tab_count;
+            ix.table = v->d_tab;
             ix.nsamples = v->nsamples;
         } else {
             ix.starts = d_starts;
             ix.counts = d_counts;
         }
-        // DDS_OVERLAP on a variable-count batch: plan + gather in a scratch slot of its own (ring of kRing)
-        const bool ovl = no_sync && (flags & DDS_OVERLAP);
-        ddsk_scratch_t *scr = &s->scr;
-        if (ovl) {
-            if (int rc = ensure_ring(s, nreq, st)) return rc;
-            scr = &s->ring[s->ring_next];
-            s->ring_next = (s->ring_next + 1) % dds_store::kRing;
-        }
-        const bool skip = ovl && chain && s->prev_overlap;
-        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, scr, (no_sync ? 0 : 2) | (ovl ? 4 : 0) | (skip ? 16 : 0),
-                              st);
-        s->prev_overlap = ovl;
-        s->pending_total_ptr = &scr->req_dst[nreq];
+        krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &scr, kflags, st);
+        s->pending_total_ptr = uses_scratch ? &scr.req_dst[nreq] : s->scr.total;
     }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
 
     s->pending_fixed_total = fixed ? upper : -1;
     s->pending_nreq = nreq;
-    s->prev_fixed = fixed;
     if (no_sync) { // nothing but the kernel(s) goes on the stream; the status word is read back in dds_batch_wait
         s->pending = true;
         s->pending_stream = st;
@@ -773,7 +945,7 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
     // ---- results back to a host destination
     if (!dst_dev) {
         if (dst_offsets && !fixed)
-            CU(cudaMemcpyAsync(dst_offsets, s->scr.req_dst, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(dst_offsets, d_offsets, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
         if (small_out) {
             CU(cudaStreamSynchronize(st));
             int64_t tot = fixed ? upper : (int64_t)s->h_status[1];
@@ -818,17 +990,18 @@ int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_st
     if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
     if (nsamples < 0 || (nsamples > 0 && (!row_start || !row_count))) return fail(DDS_ERR_ARG, "bad sample index");
     CU(cudaSetDevice(s->device));
-    if (v->d_tab_start) cudaFree(v->d_tab_start);
-    if (v->d_tab_count) cudaFree(v->d_tab_count);
-    v->d_tab_start = v->d_tab_count = nullptr;
+    if (s->pending) dds_batch_wait(s, nullptr, nullptr);
+    CU(cudaDeviceSynchronize()); // no queued launch may still be reading the old table
+    if (v->d_tab) cudaFree(v->d_tab);
+    v->d_tab = nullptr;
     v->h_tab_count.clear();
     v->nsamples = 0;
     if (nsamples == 0) return DDS_OK;
-    CU(cudaMalloc((void **)&v->d_tab_start, (size_t)nsamples * 8));
-    CU(cudaMalloc((void **)&v->d_tab_count, (size_t)nsamples * 8));
+    // the two arrays are interleaved into {start, count} pairs: the lookup of a sample id is ONE 16-byte load
+    CU(cudaMalloc((void **)&v->d_tab, (size_t)nsamples * 16));
     const cudaMemcpyKind kind = tables_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CU(cudaMemcpyAsync(v->d_tab_start, row_start, (size_t)nsamples * 8, kind, s->stream));
-    CU(cudaMemcpyAsync(v->d_tab_count, row_count, (size_t)nsamples * 8, kind, s->stream));
+    CU(cudaMemcpy2DAsync(v->d_tab, 16, row_start, 8, 8, (size_t)nsamples, kind, s->stream));
+    CU(cudaMemcpy2DAsync(v->d_tab + 1, 16, row_count, 8, 8, (size_t)nsamples, kind, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     if (!tables_on_device) v->h_tab_count.assign(row_count, row_count + nsamples); // sizes a host destination needs
     v->nsamples = nsamples;
@@ -845,7 +1018,7 @@ int dds_get_samples(dds_store_t *s, const char *name, const int64_t *sample_ids,
     Var *v = find_var(s, name);
     if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
     if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE);
-    if (!v->d_tab_start) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
+    if (!v->d_tab) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
     return batch_impl(s, v, true, sample_ids, nullptr, 0, nreq, dst, dst_capacity, dst_offsets, flags, cuda_stream,
                       total_bytes, bad_index);
 }
@@ -861,10 +1034,13 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
     if (nreq < 0 || (nreq > 0 && !sample_ids)) return fail(DDS_ERR_ARG, "bad sample ids");
     Var *vv[DDSK_MAX_MULTI];
     std::string key;
+    int64_t cap_total = 0;
     for (int v = 0; v < nvars; v++) {
         vv[v] = find_var(s, names[v]);
         if (!vv[v]) return fail(DDS_ERR_UNKNOWN_VAR, names[v] ? names[v] : "(null)");
-        if (!vv[v]->d_tab_start) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
+        if (!vv[v]->d_tab) return fail(DDS_ERR_ARG, "variable has no sample index (call dds_set_sample_index first)");
+        if (dst_capacities[v] < 0) return fail(DDS_ERR_ARG, "negative capacity");
+        cap_total += dst_capacities[v];
         key += vv[v]->name;
         key += '\n';
     }
@@ -892,40 +1068,46 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
         CU(cudaMemcpyAsync(s->d_starts, sample_ids, (size_t)nreq * 8, cudaMemcpyHostToDevice, st));
         d_ids = s->d_starts;
     }
-    if (int rc = ensure_scratch(s, nreq * nvars)) return rc;
+    const bool ovl = no_sync && (flags & DDS_OVERLAP);
+    const bool uses_scratch = ddsk_var_uses_scratch(nreq * nvars, cap_total);
+    if (uses_scratch) {
+        if (int rc = ovl ? ensure_slots(s, nreq * nvars, cap_total) : ensure_scratch(s, nreq * nvars, cap_total)) return rc;
+    }
+    // a synchronous caller wants the per-variable totals: they are the last entries of the per-variable offsets, which
+    // go to the caller's arrays or to a staging array of the store
+    const bool stage_offs = !no_sync && total_bytes != nullptr;
+    if (stage_offs) {
+        if (int rc = ensure_offs(s, (int64_t)nvars * (nreq + 1))) return rc;
+    }
     ddsk_multi_t m;
     memset(&m, 0, sizeof(m));
     m.nvars = nvars;
     m.vars_dev = s->d_multi_vars;
     for (int v = 0; v < nvars; v++) {
-        m.table_start[v] = vv[v]->d_tab_start;
-        m.table_count[v] = vv[v]->d_tab_count;
+        m.table[v] = vv[v]->d_tab;
         m.nsamples[v] = vv[v]->nsamples;
         m.dst[v] = dsts[v];
         m.cap[v] = dst_capacities[v];
-        m.offsets[v] = dst_offsets ? dst_offsets[v] : nullptr;
+        m.offsets[v] = dst_offsets && dst_offsets[v] ? dst_offsets[v] : (stage_offs ? s->d_offs + (int64_t)v * (nreq + 1) : nullptr);
     }
-    if (ddsk_gather_multi(&m, d_ids, nreq, &s->scr, no_sync ? 0 : 2, st)) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
-    s->prev_overlap = false;
-    s->prev_fixed = false;
+    const int kflags = (no_sync ? 0 : DDSK_F_MIRROR) | overlap_flags(s, ovl, chain);
+    ddsk_scratch_t scr = scratch_view(s, uses_scratch && ovl);
+    if (ddsk_gather_multi(&m, d_ids, nreq, &scr, kflags, st)) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
     s->pending_fixed_total = -1;
     s->pending_nreq = nreq * nvars;
-    s->pending_total_ptr = &s->scr.req_dst[nreq * nvars];
+    s->pending_total_ptr = uses_scratch ? &scr.req_dst[nreq * nvars] : s->scr.total;
     if (no_sync) {
         s->pending = true;
         s->pending_stream = st;
         return DDS_OK;
     }
-    // per-variable totals = differences of the plan offsets at the variable boundaries
     int64_t *hb = (int64_t *)s->h_small;
-    for (int v = 1; v < nvars; v++)
-        CU(cudaMemcpyAsync(&hb[v], &s->scr.req_dst[(int64_t)v * nreq], 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    hb[0] = 0;
-    hb[nvars] = (int64_t)s->h_status[1];
     if (total_bytes)
-        for (int v = 0; v < nvars; v++) total_bytes[v] = hb[v + 1] - hb[v];
+        for (int v = 0; v < nvars; v++) CU(cudaMemcpyAsync(&hb[v], m.offsets[v] + nreq, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     int rc = decode_status(s, st, s->h_status[0], bad_index);
+    if (total_bytes)
+        for (int v = 0; v < nvars; v++) total_bytes[v] = rc == DDS_ERR_CAPACITY ? 0 : hb[v];
     if (bad_index && *bad_index >= 0) *bad_index %= nreq; // index of the sample in the id list
     return rc;
 }
@@ -935,13 +1117,13 @@ int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
     if (!s) return fail(DDS_ERR_ARG, "null store");
     if (!s->pending) return DDS_OK;
     s->pending = false;
+    s->run_len = 0;
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->pending_stream;
     // queued launches skip the host mirror (it costs ~2 us at the end of every kernel): read the words back here
     CU(cudaMemcpyAsync(&s->h_status[0], s->scr.status, 8, cudaMemcpyDeviceToHost, st));
-    if (s->pending_fixed_total < 0)
-        CU(cudaMemcpyAsync(&s->h_status[1], s->pending_total_ptr ? s->pending_total_ptr : &s->scr.req_dst[s->pending_nreq], 8,
-                           cudaMemcpyDeviceToHost, st));
+    if (s->pending_fixed_total < 0 && s->pending_total_ptr)
+        CU(cudaMemcpyAsync(&s->h_status[1], s->pending_total_ptr, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (total_bytes) *total_bytes = s->pending_fixed_total >= 0 ? s->pending_fixed_total : (int64_t)s->h_status[1];
     return decode_status(s, st, s->h_status[0], bad_index);
@@ -949,7 +1131,7 @@ int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index) {
 
 int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int itemsize, void *buffer,
             int buffer_on_device) {
-    // one request through the batch path: same kernel, same checks (ddstore.hpp:197-238)
+    // one request through the batch entry: same checks (ddstore.hpp:197-238); small results take the 1-CTA kernel
     if (!s) return fail(DDS_ERR_ARG, "null store");
     Var *v = find_var(s, name);
     if (!v) {
@@ -986,6 +1168,7 @@ int dds_epoch_begin(dds_store_t *s) {
         if (x.second.fence_active) return fail(DDS_ERR_FENCE_ACTIVE);
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    if (int rc = drain_update_streams(s)) return rc; // dds_update_async copies on caller streams are part of the epoch
     if (int rc = dds_comm_barrier(s->comm)) return rc;
     for (auto &x : s->vars) x.second.fence_active = true;
     return DDS_OK;
@@ -1000,6 +1183,7 @@ int dds_epoch_end(dds_store_t *s) {
     CU(cudaSetDevice(s->device));
     if (s->pending) dds_batch_wait(s, nullptr, nullptr);
     CU(cudaStreamSynchronize(s->stream));
+    if (int rc = drain_update_streams(s)) return rc;
     if (int rc = dds_comm_barrier(s->comm)) return rc;
     for (auto &x : s->vars) x.second.fence_active = false;
     return DDS_OK;
@@ -1016,6 +1200,7 @@ int dds_free(dds_store_t *s) {
     if (s->vars.empty() && s->zombies.empty() && s->zombie_blocks.empty()) return DDS_OK;
     CU(cudaSetDevice(s->device));
     if (s->pending) dds_batch_wait(s, nullptr, nullptr);
+    s->update_streams.clear();
     CU(cudaDeviceSynchronize());
     int rc = dds_comm_barrier(s->comm); // nobody is reading any more
     local_release(s);
@@ -1032,7 +1217,14 @@ int dds_free(dds_store_t *s) {
 
 void dds_destroy(dds_store_t *s) {
     if (!s) return;
-    // non-collective local teardown (the collective one is dds_free)
+    // Teardown of this rank's handle. The reference's destructor runs the collective free() (ddstore.cxx:41-44); here
+    // peers that imported a shard as a VMM handle hold their own reference to the memory, so a local release is safe
+    // for them. Shards that peers read through a raw pointer (thread-ranks) or a legacy IPC mapping have no such
+    // protection: if any is still registered, go through the collective dds_free first so that no peer can fault on
+    // memory this rank is about to release (the communicator's own timeout bounds the wait if a peer is gone).
+    bool unprotected = false;
+    for (auto &x : s->vars) unprotected |= x.second.unprotected_peers;
+    if (unprotected && s->size > 1) (void)dds_free(s);
     if (cudaSetDevice(s->device) == cudaSuccess) {
         cudaDeviceSynchronize();
         local_release(s);
@@ -1044,18 +1236,20 @@ void dds_destroy(dds_store_t *s) {
         if (s->scr.req_src) cudaFree(s->scr.req_src);
         if (s->scr.req_dst) cudaFree(s->scr.req_dst);
         if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
+        if (s->scr.seg_tab) cudaFree(s->scr.seg_tab);
+        for (auto &sl : s->slots) {
+            if (sl.req_src) cudaFree(sl.req_src);
+            if (sl.req_dst) cudaFree(sl.req_dst);
+            if (sl.tile_sums) cudaFree(sl.tile_sums);
+            if (sl.seg_tab) cudaFree(sl.seg_tab);
+        }
         if (s->d_starts) cudaFree(s->d_starts);
         if (s->d_counts) cudaFree(s->d_counts);
         if (s->d_out) cudaFree(s->d_out);
+        if (s->d_offs) cudaFree(s->d_offs);
         if (s->h_status) cudaFreeHost(s->h_status);
         if (s->h_small) cudaFreeHost(s->h_small);
         if (s->d_multi_vars) cudaFree(s->d_multi_vars);
-        for (int k = 0; k < dds_store::kRing; k++) {
-            if (s->ring[k].req_src) cudaFree(s->ring[k].req_src);
-            if (s->ring[k].req_dst) cudaFree(s->ring[k].req_dst);
-            if (s->ring[k].tile_sums) cudaFree(s->ring[k].tile_sums);
-            if (s->ring[k].counters) cudaFree(s->ring[k].counters);
-        }
         if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();
@@ -1072,6 +1266,38 @@ int dds_synth_fill(dds_store_t *s, const char *name, uint64_t seed) {
     if (ddsk_synth_fill(v->base, first, v->nrows, v->disp, v->itemsize, seed, s->stream))
         return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
     CU(cudaStreamSynchronize(s->stream));
+    return DDS_OK;
+}
+
+int dds_synth_verify(dds_store_t *s, const char *name, const void *packed_dev, const int64_t *starts_dev,
+                     const int64_t *counts_dev, int64_t fixed_count, const int64_t *offsets_dev, int64_t nreq, uint64_t seed,
+                     void *cuda_stream, uint64_t *result) {
+    clear_error();
+    if (!s || !result) return fail(DDS_ERR_ARG, "null store or result");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    const size_t words = 2 + DDSK_MAX_RANKS;
+    unsigned long long *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, words * 8));
+    cudaError_t e = cudaMemsetAsync(d_out, 0, words * 8, st);
+    int krc = 0;
+    if (e == cudaSuccess)
+        krc = ddsk_synth_verify(&v->kv, packed_dev, starts_dev, counts_dev, fixed_count, offsets_dev, nreq, v->disp, v->itemsize,
+                                seed, d_out, st);
+    if (e == cudaSuccess && !krc) e = cudaMemcpyAsync(result, d_out, words * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !krc) e = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    if (e != cudaSuccess) return cuda_fail(e, "dds_synth_verify");
+    return DDS_OK;
+}
+
+int dds_test_occupy(int device, int ctas, int smem_bytes, uint64_t nanoseconds, void *cuda_stream) {
+    clear_error();
+    CU(cudaSetDevice(device));
+    if (ddsk_occupy(ctas, smem_bytes, nanoseconds, cuda_stream)) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
     return DDS_OK;
 }
 

@@ -238,8 +238,12 @@ void release(Block *b) {
 
 // Every rank hands `my_fd` to each rank r with want[r] != 0 and receives one descriptor from each such rank
 // (want is symmetric: ranks of other processes on this host). COLLECTIVE over `comm` (two barriers).
+// The sockets live in the abstract namespace under a name derived from a random job token; every datagram is checked
+// against the kernel-supplied sender credentials (SO_PASSCRED: same uid, and the pid that rank published in the
+// bootstrap all-gather), so another local process can neither inject a descriptor nor impersonate a rank; messages
+// that fail the check are dropped. A rank whose export failed sends "no descriptor" (my_fd < 0) explicitly.
 int exchange_fds(dds_comm_t *comm, const std::string &tag, int my_fd, const std::vector<char> &want,
-                 std::vector<int> *got) {
+                 const std::vector<int> &pids, std::vector<int> *got) {
     const int rank = dds_comm_rank(comm), size = dds_comm_size(comm);
     got->assign((size_t)size, -1);
     int expect = 0;
@@ -249,15 +253,21 @@ int exchange_fds(dds_comm_t *comm, const std::string &tag, int my_fd, const std:
     socklen_t alen;
     sockaddr_un me = abstract_addr(tag + "-" + std::to_string(rank), &alen);
     int rc = DDS_OK;
-    if (bind(sock, (sockaddr *)&me, alen) != 0) rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: bind() failed");
+    int one = 1;
+    if (setsockopt(sock, SOL_SOCKET, SO_PASSCRED, &one, sizeof(one)) != 0)
+        rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: SO_PASSCRED failed");
+    if (!rc && bind(sock, (sockaddr *)&me, alen) != 0) rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: bind() failed");
     int brc = dds_comm_barrier(comm); // every socket is bound before anyone sends
     if (!rc) rc = brc;
+    struct Msg {
+        int32_t rank, has_fd;
+    };
     if (!rc) {
         for (int r = 0; r < size && !rc; r++) {
             if (r == rank || !want[(size_t)r]) continue;
             socklen_t plen;
             sockaddr_un peer = abstract_addr(tag + "-" + std::to_string(r), &plen);
-            int32_t payload = rank;
+            Msg payload = {rank, my_fd >= 0 ? 1 : 0};
             iovec iov = {&payload, sizeof(payload)};
             char ctrl[CMSG_SPACE(sizeof(int))];
             memset(ctrl, 0, sizeof(ctrl));
@@ -267,42 +277,60 @@ int exchange_fds(dds_comm_t *comm, const std::string &tag, int my_fd, const std:
             msg.msg_namelen = plen;
             msg.msg_iov = &iov;
             msg.msg_iovlen = 1;
-            msg.msg_control = ctrl;
-            msg.msg_controllen = sizeof(ctrl);
-            cmsghdr *c = CMSG_FIRSTHDR(&msg);
-            c->cmsg_level = SOL_SOCKET;
-            c->cmsg_type = SCM_RIGHTS;
-            c->cmsg_len = CMSG_LEN(sizeof(int));
-            memcpy(CMSG_DATA(c), &my_fd, sizeof(int));
+            if (my_fd >= 0) {
+                msg.msg_control = ctrl;
+                msg.msg_controllen = sizeof(ctrl);
+                cmsghdr *c = CMSG_FIRSTHDR(&msg);
+                c->cmsg_level = SOL_SOCKET;
+                c->cmsg_type = SCM_RIGHTS;
+                c->cmsg_len = CMSG_LEN(sizeof(int));
+                memcpy(CMSG_DATA(c), &my_fd, sizeof(int));
+            }
             if (sendmsg(sock, &msg, 0) < 0) rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: sendmsg() failed");
         }
-        for (int k = 0; k < expect && !rc; k++) {
+        std::vector<char> seen((size_t)size, 0);
+        for (int k = 0; k < expect && !rc;) {
             pollfd pf = {sock, POLLIN, 0};
             if (poll(&pf, 1, 120000) <= 0) {
                 rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: timed out waiting for a peer's descriptor");
                 break;
             }
-            int32_t from = -1;
+            Msg from = {-1, 0};
             iovec iov = {&from, sizeof(from)};
-            char ctrl[CMSG_SPACE(sizeof(int))];
+            char ctrl[CMSG_SPACE(sizeof(int)) + CMSG_SPACE(sizeof(struct ucred))];
             msghdr msg;
             memset(&msg, 0, sizeof(msg));
             msg.msg_iov = &iov;
             msg.msg_iovlen = 1;
             msg.msg_control = ctrl;
             msg.msg_controllen = sizeof(ctrl);
-            if (recvmsg(sock, &msg, MSG_CMSG_CLOEXEC) < 0) {
+            ssize_t n = recvmsg(sock, &msg, MSG_CMSG_CLOEXEC);
+            if (n < 0) {
                 rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: recvmsg() failed");
                 break;
             }
-            cmsghdr *c = CMSG_FIRSTHDR(&msg);
-            if (!c || c->cmsg_type != SCM_RIGHTS || from < 0 || from >= size) {
-                rc = dds_internal::fail(DDS_ERR_COMM, "fd exchange: malformed message");
-                break;
+            int fd = -1;
+            bool have_cred = false;
+            struct ucred cred;
+            memset(&cred, 0, sizeof(cred));
+            for (cmsghdr *c = CMSG_FIRSTHDR(&msg); c; c = CMSG_NXTHDR(&msg, c)) {
+                if (c->cmsg_level != SOL_SOCKET) continue;
+                if (c->cmsg_type == SCM_RIGHTS && c->cmsg_len >= CMSG_LEN(sizeof(int))) memcpy(&fd, CMSG_DATA(c), sizeof(int));
+                if (c->cmsg_type == SCM_CREDENTIALS && c->cmsg_len >= CMSG_LEN(sizeof(struct ucred))) {
+                    memcpy(&cred, CMSG_DATA(c), sizeof(cred));
+                    have_cred = true;
+                }
             }
-            int fd;
-            memcpy(&fd, CMSG_DATA(c), sizeof(int));
-            (*got)[(size_t)from] = fd;
+            const bool ok = n == (ssize_t)sizeof(from) && have_cred && cred.uid == geteuid() && from.rank >= 0 &&
+                            from.rank < size && from.rank != rank && want[(size_t)from.rank] && !seen[(size_t)from.rank] &&
+                            (int)cred.pid == pids[(size_t)from.rank] && (from.has_fd != 0) == (fd >= 0);
+            if (!ok) { // not one of ours (or a duplicate): drop it, keep waiting for the real peer
+                if (fd >= 0) close(fd);
+                continue;
+            }
+            seen[(size_t)from.rank] = 1;
+            (*got)[(size_t)from.rank] = fd; // -1: the peer had nothing to export
+            k++;
         }
     }
     brc = dds_comm_barrier(comm); // nobody closes its socket while a peer may still be sending to it

@@ -25,8 +25,9 @@ int export_fd(Block *b);
 int grant(const Block *b, int device); // let another device of THIS process read/write the block
 int import_fd(int device, int fd, size_t size, Block *out);
 void release(Block *b);
+// my_fd < 0: nothing to export (sent explicitly); pids[r] = process id rank r published (sender verification)
 int exchange_fds(dds_comm_t *comm, const std::string &tag, int my_fd, const std::vector<char> &want,
-                 std::vector<int> *got);
+                 const std::vector<int> &pids, std::vector<int> *got);
 
 } // namespace dds_vmm
 #endif

@@ -204,7 +204,7 @@ class PyDDStore:
         _capi.raise_for(rc)
         return total.value
 
-    def get_samples_multi(self, names, sample_ids, outs, offsets=None, stream=None, wait=True):
+    def get_samples_multi(self, names, sample_ids, outs, offsets=None, stream=None, wait=True, overlap=False):
         """The rows of the same samples in several variables (<= 4, each with a sample index) in ONE launch:
         outs[v] (CUDA tensors) receive variable names[v]'s packed rows, offsets[v] (optional int64 CUDA tensors of
         len(ids)+1) the per-sample byte offsets. Returns the list of packed sizes (None when wait=False)."""
@@ -219,6 +219,8 @@ class PyDDStore:
             sa = _i64(sample_ids)
             nreq, sp, keep = sa.size, sa.ctypes.data, sa
         flags = (_capi.IDX_ON_DEVICE if s_dev else 0) | _capi.DST_ON_DEVICE | (0 if wait else _capi.NO_SYNC)
+        if overlap and not wait:
+            flags |= _capi.OVERLAP
         c_names = (C.c_char_p * nv)(*[n.encode() for n in names])
         c_dsts = (C.c_void_p * nv)(*[o.ptr for o in obs])
         c_caps = (C.c_int64 * nv)(*[o.nbytes for o in obs])
@@ -263,6 +265,16 @@ class PyDDStore:
 
     def synth_fill(self, name, seed):
         _capi.raise_for(self._L.dds_synth_fill(self._h, name.encode(), int(seed)))
+
+    def synth_verify(self, name, packed, starts, counts=None, count=1, offsets=None, seed=0, stream=None):
+        """Check a packed batch (CUDA tensors) of variable `name` -- filled by synth_fill(name, seed) -- against the
+        generator on the device. Returns (mismatching elements, rows checked, requests per owner rank)."""
+        res = (C.c_uint64 * 66)()
+        _capi.raise_for(self._L.dds_synth_verify(
+            self._h, name.encode(), packed.data_ptr(), starts.data_ptr(), counts.data_ptr() if counts is not None else None,
+            int(count), offsets.data_ptr() if offsets is not None else None, starts.numel(), int(seed),
+            self._stream_arg(stream), res))
+        return int(res[0]), int(res[1]), [int(res[2 + r]) for r in range(self.size)]
 
     def close(self):
         """non-collective teardown of this rank's handle (the collective one is free())"""

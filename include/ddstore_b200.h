@@ -116,7 +116,9 @@ int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nro
 int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
                      int buffer_on_device, void *cuda_stream);
 /* template<T> void get(string name, long start, long count, T* buffer), ddstore.hpp:197-248. Fetches
- * count rows starting at GLOBAL row `start` (must lie within one owner) into `buffer` (host, or device). */
+ * count rows starting at GLOBAL row `start` (must lie within one owner) into `buffer` (host, or device).
+ * Results up to 64 KiB (host) / 1 MiB (device) take a 1-CTA kernel whose completion the host spins on in mapped
+ * pinned memory: one launch, no stream synchronize (the legacy one-get-per-sample loader loop). */
 int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int itemsize, void *buffer,
             int buffer_on_device);
 
@@ -131,11 +133,14 @@ int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int 
 #define DDS_IDX_ON_DEVICE 1u /* starts / counts are device pointers */
 #define DDS_DST_ON_DEVICE 2u /* dst / dst_offsets are device pointers */
 #define DDS_NO_SYNC 4u       /* needs both flags above: enqueue on cuda_stream and return; dds_batch_wait() reports */
-#define DDS_OVERLAP 8u       /* with DDS_NO_SYNC: this batch is INDEPENDENT of the batch queued just before it on the same
-                              * stream (different destination / offsets buffers; indices not produced by it), so the
+#define DDS_OVERLAP 8u       /* with DDS_NO_SYNC: this batch is INDEPENDENT of the ONE batch queued just before it on the
+                              * same stream (different destination / offsets buffers; indices not produced by it), so the
                               * two may overlap: the head of this one fills the SMs the tail of the previous one vacates
-                              * (double-buffered prefetch). Variable-count batches then plan in a scratch slot of
-                              * their own. Ignored when it does not apply. */
+                              * (double-buffered prefetch). The contract is enforced by the kernel, not assumed: batch q
+                              * writes nothing before batch q-2 has retired (so reusing the buffers of batch q-2 is safe
+                              * whatever else shares the GPU), and batches retire in order (whatever follows batch q on
+                              * the stream sees all earlier ones complete). Honoured for fixed-count batches and for
+                              * variable-count batches of <= 8192 requests into < 4 GiB; ignored otherwise. */
 int dds_get_batch(dds_store_t *s, const char *name, const int64_t *starts, const int64_t *counts,
                   int64_t fixed_count, int64_t nreq, int itemsize, void *dst, int64_t dst_capacity,
                   int64_t *dst_offsets, unsigned flags, void *cuda_stream, int64_t *total_bytes,
@@ -176,6 +181,16 @@ int dds_free(dds_store_t *s);
 /* Fill this rank's shard of `name` with the synthetic payload of SURVEY.md 8d, on device:
  * element (global_row g, col c) = low itemsize bytes of splitmix64(seed ^ (g*disp + c)). */
 int dds_synth_fill(dds_store_t *s, const char *name, uint64_t seed);
+/* Check a packed batch against that generator ON THE DEVICE: request i = rows [starts[i], + counts[i] or fixed_count) of
+ * `name`, its bytes at packed + (offsets ? offsets[i] : i * fixed_count * disp * itemsize); all pointers device memory
+ * (counts / offsets nullable). result[0] = mismatching elements, result[1] = rows checked, result[2 + r] = requests
+ * owned by rank r (66 words, host memory). Synchronous. */
+int dds_synth_verify(dds_store_t *s, const char *name, const void *packed_dev, const int64_t *starts_dev,
+                     const int64_t *counts_dev, int64_t fixed_count, const int64_t *offsets_dev, int64_t nreq, uint64_t seed,
+                     void *cuda_stream, uint64_t *result);
+/* Test helper: occupy `ctas` SMs' worth of shared memory (`smem_bytes` per CTA) for `nanoseconds` on `cuda_stream` --
+ * a stand-in for a training kernel sharing the GPU with a prefetch queue. */
+int dds_test_occupy(int device, int ctas, int smem_bytes, uint64_t nanoseconds, void *cuda_stream);
 /* kernels launched by this library since load, and the gather launch geometry in use */
 unsigned long long dds_kernel_launches(void);
 void dds_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes);

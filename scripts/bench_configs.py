@@ -111,6 +111,15 @@ def main():
             offs = torch.empty(B + 1, dtype=torch.int64, device=dev)
             timed(lambda: store.get_batch("x", st, ct, out=out, offsets=offs, stream=side.cuda_stream, wait=False), nbytes,
                   f"cfg3 variable 100-10000 f32 (4-byte aligned rows), B={B}", {"samples": nsamp})
+            out_c, offs_c = torch.empty_like(out), torch.empty_like(offs)
+            flipc = [0]
+
+            def queued_explicit():
+                flipc[0] ^= 1
+                store.get_batch("x", st, ct, out=out_c if flipc[0] else out, offsets=offs_c if flipc[0] else offs,
+                                stream=side.cuda_stream, wait=False, overlap=True)
+
+            timed(queued_explicit, nbytes, f"cfg3 explicit, DDS_OVERLAP double-buffered queue, B={B}", {"samples": nsamp})
             if B == 4096:
                 store.set_sample_index("x", d_start, d_len)
             timed(lambda: store.get_samples("x", ids, out, offsets=offs, stream=side.cuda_stream, wait=False), nbytes,
@@ -158,6 +167,15 @@ def main():
             timed(lambda: store.get_samples_multi(["node_feat", "edge_index"], ids, [o1, o2], stream=side.cuda_stream,
                                                   wait=False),
                   b1 + b2, f"cfg4 both arrays by sample id in ONE launch, B={B}", {"samples": nsamp})
+            p1, p2 = torch.empty_like(o1), torch.empty_like(o2)
+            flip4 = [0]
+
+            def queued4():
+                flip4[0] ^= 1
+                store.get_samples_multi(["node_feat", "edge_index"], ids, [p1, p2] if flip4[0] else [o1, o2],
+                                        stream=side.cuda_stream, wait=False, overlap=True)
+
+            timed(queued4, b1 + b2, f"cfg4 ONE launch, DDS_OVERLAP double-buffered queue, B={B}", {"samples": nsamp})
         store.free()
         store = PyDDStore(comm, device=local)
 

@@ -428,14 +428,14 @@ rng = np.random.default_rng(77)
 shard = rng.integers(0, 256, size=(60000, 3), dtype=np.uint8)
 store = PyDDStore(device=0)
 store.add("b", shard)
-for B in (300, 9000, 70000):
+for B in (300, 4096, 5000, 8192, 9000, 70000):
     starts, counts = random_valid_requests(rng, [60000], B, max_count=30)
     exp, exp_offs, bad, _ = COracle().get_batch([shard], starts, counts)
     out = np.zeros(max(exp.size, 1), np.uint8)
     offs = np.zeros(B + 1, np.int64)
     assert store.get_batch("b", starts, counts, out=out, offsets=offs) == exp.size
     assert out[:exp.size].tobytes() == exp.tobytes() and offs.tolist() == exp_offs.tolist(), B
-    starts[B // 2] = 60000  # first bad request in the middle
+    starts[B // 2], counts[B // 2] = 60000, 1  # first bad request in the middle
     try:
         store.get_batch("b", starts, counts, out=out)
         raise SystemExit("no error raised")
@@ -446,16 +446,17 @@ print("plan-ok")
 """
 
 
-@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("mode", ["0", "1"])
 def test_plan_variants_agree(tmp_path, mode):
-    """DDS_FUSED_PLAN=0 (separate plan kernels) and =2 (in-kernel plan at every size) against the oracle"""
+    """DDS_SMEM_PLAN=0 (plan kernels + segment table at every size) and =1 (every CTA plans <= 8192 requests in its
+    own shared memory) against the oracle"""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "plan_variant.py"
     script.write_text(PLAN_SCRIPT.format(root=root))
-    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_FUSED_PLAN=mode), capture_output=True,
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_SMEM_PLAN=mode), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "plan-ok" in r.stdout, r.stdout + r.stderr
 
@@ -650,3 +651,136 @@ def test_overlapped_queue_of_variable_count_batches(coracle):
         return True
 
     assert all(run_world(1, body))
+
+
+OVERLAP_SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r})
+import ctypes
+import numpy as np, torch
+from ddstore_b200 import PyDDStore, _capi
+rng = np.random.default_rng(77)
+shard = rng.integers(0, 2**32, size=(150_000, 256), dtype=np.uint32).view(np.float32)   # 1 KiB rows
+L = rng.integers(1, 40, size=20_000)
+sstart = np.concatenate([[0], np.cumsum(L)])
+vshard = rng.integers(0, 2**32, size=(int(sstart[-1]), 5), dtype=np.uint32).view(np.float32)  # 20 B rows: re-phase path
+store = PyDDStore(device=0)
+store.add("x", shard)
+store.add("v", vshard)
+store.set_sample_index("v", sstart[:-1], L)
+dev = torch.device("cuda", 0)
+side, other = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+B = 30_000
+bufs = [torch.zeros((B, 256), dtype=torch.float32, device=dev) for _ in range(2)]
+vcap = int(L.max()) * 20 * 4096 + 64
+vbufs = [torch.zeros(vcap, dtype=torch.uint8, device=dev) for _ in range(2)]
+lib = _capi.lib()
+for rnd in range(8):
+    nb = 5 + rnd % 3
+    batches = [rng.integers(0, 150_000, size=B) for _ in range(nb)]
+    d_idx = [torch.from_numpy(b).to(dev) for b in batches]
+    vids = [rng.integers(0, 20_000, size=4096) for _ in range(nb)]
+    d_vid = [torch.from_numpy(b).to(dev) for b in vids]
+    torch.cuda.synchronize()
+    # a "training kernel" on another stream takes about half of the SMs away for the whole queue
+    _capi.raise_for(lib.dds_test_occupy(0, 70 + rnd, 200 * 1024, 3_000_000, ctypes.c_void_p(other.cuda_stream)))
+    for k in range(nb):
+        store.get_batch("x", d_idx[k], out=bufs[k & 1], count=1, stream=side.cuda_stream, wait=False, overlap=True)
+    store.wait()
+    for slot, k in (((nb - 1) & 1, nb - 1), ((nb - 2) & 1, nb - 2)):
+        assert bufs[slot].cpu().numpy().tobytes() == shard[batches[k]].tobytes(), ("fixed", rnd, slot, k)
+    _capi.raise_for(lib.dds_test_occupy(0, 70 + rnd, 200 * 1024, 2_000_000, ctypes.c_void_p(other.cuda_stream)))
+    for k in range(nb):
+        store.get_samples("v", d_vid[k], vbufs[k & 1], stream=side.cuda_stream, wait=False, overlap=True)
+    store.wait()
+    for slot, k in (((nb - 1) & 1, nb - 1), ((nb - 2) & 1, nb - 2)):
+        exp = np.concatenate([vshard[sstart[i]:sstart[i] + L[i]].reshape(-1) for i in vids[k]]).view(np.uint8)
+        assert vbufs[slot][:exp.size].cpu().numpy().tobytes() == exp.tobytes(), ("var", rnd, slot, k)
+    torch.cuda.synchronize()
+store.free(); store.close()
+print("overlap-ok")
+"""
+
+
+@pytest.mark.parametrize("ctas_per_sm", ["1", "2"])
+def test_overlap_contract_holds_when_the_gpu_is_shared(tmp_path, ctas_per_sm):
+    """DDS_OVERLAP is a contract the kernel enforces (generation words), not a capacity assumption: a double-buffered
+    overlapped queue stays correct while another kernel holds half of the SMs, and with 2 gather CTAs per SM."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "overlap_contract.py"
+    script.write_text(OVERLAP_SCRIPT.format(root=root))
+    env = dict(os.environ, DDS_GATHER_CTAS_PER_SM=ctas_per_sm)
+    if ctas_per_sm == "2":
+        env["DDS_GATHER_GEOM"] = "5"  # 4 warps x 6 stages: two CTAs fit on an SM
+        env["DDS_GATHER_GEOM_S"] = "4"
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "overlap-ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_negative_and_zero_fixed_count(coracle):
+    """a negative fixed count is the reference's 'Invalid count on target' on request 0 -- unless request 0's start is
+    invalid, which is checked first (ddstore.hpp:210-214); count 0 copies nothing and succeeds"""
+    torch = _torch()
+    shards = [np.arange(40, dtype=np.int64).reshape(10, 4), np.arange(40, 80, dtype=np.int64).reshape(10, 4)]
+
+    def body(store, r):
+        store.add("x", shards[r])
+        out = np.zeros((8, 4), np.int64)
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.get_batch("x", [3, 4, 5], out=out, count=-1)
+        assert store.last_bad_index == 0
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.get_batch("x", torch.tensor([3, 4, 5]).cuda(), out=torch.zeros(64, dtype=torch.int64).cuda(), count=-2)
+        assert store.last_bad_index == 0
+        assert store.get_batch("x", [3, 4, 5], out=out, count=0) == 0 and not out.any()
+        from ddstore_b200 import _capi
+        with pytest.raises(ValueError, match="Invalid count on target"):  # the single-request entry (1-CTA kernel)
+            _capi.raise_for(store._L.dds_get(store._h, b"x", 3, -1, 8, out.ctypes.data, 0))
+        return True
+
+    assert all(run_world(2, body))
+
+
+def test_single_request_kernel_alignments_and_errors(coracle):
+    """dds_get's 1-CTA kernel: every source/destination alignment class (16 / 4 / 1 byte), host and device
+    destinations, remote owners, zero rows, and the reference's two errors"""
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    shards = [rng.integers(0, 256, size=(n, 3), dtype=np.uint8) for n in (301, 0, 407)]
+    f32 = [rng.integers(0, 2**32, size=(n, 5), dtype=np.uint32).view(np.float32) for n in (64, 64, 64)]
+    allb = np.concatenate(shards)
+    allf = np.concatenate(f32)
+
+    def body(store, r):
+        store.add("b", shards[r])
+        store.add("f", f32[r])
+        for start, cnt in ((0, 1), (299, 2), (301, 7), (500, 208), (707, 1), (3, 0)):
+            if start + cnt > 708 or (start < 301 < start + cnt):
+                continue
+            out = np.zeros((cnt, 3), np.uint8)
+            store.get("b", out, start)
+            assert out.tobytes() == allb[start:start + cnt].tobytes(), (start, cnt)
+            dout = torch.zeros((cnt + 1, 3), dtype=torch.uint8, device="cuda")[1:].contiguous() if cnt else torch.zeros((0, 3), dtype=torch.uint8, device="cuda")
+            store.get("b", dout, start)
+            assert dout.cpu().numpy().tobytes() == allb[start:start + cnt].tobytes()
+        for start, cnt in ((0, 4), (63, 1), (64, 64), (130, 31)):
+            out = np.zeros((cnt, 5), np.float32)
+            store.get("f", out, start)
+            assert out.tobytes() == allf[start:start + cnt].tobytes()
+            big = torch.zeros(cnt * 5 + 3, dtype=torch.float32, device="cuda")
+            view = big[3:].view(cnt, 5)  # 12-byte phase relative to the allocation
+            store.get("f", view, start)
+            assert view.cpu().numpy().tobytes() == allf[start:start + cnt].tobytes()
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.get("b", np.zeros((5, 3), np.uint8), 299)  # straddles ranks 0 -> 2
+        with pytest.raises(ValueError, match="Invalid count on target"):
+            store.get("b", np.zeros((2, 3), np.uint8), 707)
+        out = np.zeros((1, 3), np.uint8)
+        store.get("b", out, 300)  # the call after an error works (no sticky state)
+        assert out.tobytes() == allb[300:301].tobytes()
+        return True
+
+    assert all(run_world(3, body))
