@@ -41,17 +41,38 @@ class _Comm:
             _capi.lib().dds_comm_free(self.handle)
             self.handle = None
 
+    def Split(self, color, key):
+        """MPI_Comm_split: the ranks that pass the same `color` form a new communicator, ordered by `key` (ties by
+        old rank). COLLECTIVE over this communicator. The reference builds its replica groups this way
+        (examples/vae/distdataset.py:28: comm.Split(rank // ddstore_width, rank))."""
+        me = (int(color), int(key), self.Get_rank())
+        parts = self.allgather_bytes(b"".join(int(x).to_bytes(8, "little", signed=True) for x in me))
+        rows = [tuple(int.from_bytes(p[i * 8:(i + 1) * 8], "little", signed=True) for i in range(3)) for p in parts]
+        members = sorted((k, r) for (c, k, r) in rows if c == int(color))
+        return self._sub([r for _, r in members], int(color))
+
+    def _sub(self, old_ranks, color):
+        raise NotImplementedError(f"{type(self).__name__} cannot be split")
+
 
 class SelfComm(_Comm):
     def __init__(self):
         self.handle = _capi.lib().dds_comm_self()
 
+    def _sub(self, old_ranks, color):
+        return SelfComm()
+
 
 class ShmComm(_Comm):
     def __init__(self, key, rank, size):
-        self.handle = _capi.lib().dds_comm_shm(str(key).encode(), int(rank), int(size))
+        self.key = str(key)
+        self.handle = _capi.lib().dds_comm_shm(self.key.encode(), int(rank), int(size))
         if not self.handle:
             raise RuntimeError(_capi.last_error())
+
+    def _sub(self, old_ranks, color):
+        # a fresh shm rendezvous per colour, named after the parent's key
+        return ShmComm(f"{self.key}.c{color}", old_ranks.index(self.Get_rank()), len(old_ranks))
 
 
 class CallbackComm(_Comm):
@@ -91,6 +112,7 @@ class TorchDistComm(CallbackComm):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        self._group = group
         rank, size = dist.get_rank(group), dist.get_world_size(group)
         on_cuda = dist.get_backend(group) == "nccl"
 
@@ -106,6 +128,21 @@ class TorchDistComm(CallbackComm):
 
         super().__init__(rank, size, allgather, barrier)
 
+    def Split(self, color, key):
+        import torch.distributed as dist
+        me = (int(color), int(key), self.Get_rank())
+        parts = self.allgather_bytes(b"".join(int(x).to_bytes(8, "little", signed=True) for x in me))
+        rows = [tuple(int.from_bytes(p[i * 8:(i + 1) * 8], "little", signed=True) for i in range(3)) for p in parts]
+        mine = None
+        # new_group is collective over the WHOLE default group: every rank creates every colour's group, in one order
+        for c in sorted({c for (c, _, _) in rows}):
+            local = [r for _, r in sorted((k, r) for (cc, k, r) in rows if cc == c)]
+            ranks = local if self._group is None else [dist.get_global_rank(self._group, r) for r in local]
+            g = dist.new_group(ranks=ranks)
+            if c == int(color):
+                mine = g
+        return TorchDistComm(mine)
+
 
 def as_dds_comm(obj):
     """Coerce what a caller passes as `comm` into a communicator object with a `.handle`."""
@@ -115,5 +152,8 @@ def as_dds_comm(obj):
         return obj
     if all(hasattr(obj, a) for a in ("Get_rank", "Get_size", "allgather", "Barrier")):
         # mpi4py.MPI.Comm and look-alikes
-        return CallbackComm(obj.Get_rank(), obj.Get_size(), lambda b: list(obj.allgather(b)), obj.Barrier)
+        c = CallbackComm(obj.Get_rank(), obj.Get_size(), lambda b: list(obj.allgather(b)), obj.Barrier)
+        if hasattr(obj, "Split"):
+            c.Split = lambda color, key: as_dds_comm(obj.Split(color, key))
+        return c
     raise TypeError(f"cannot use {type(obj).__name__} as a DDStore communicator")

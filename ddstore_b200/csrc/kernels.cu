@@ -176,6 +176,14 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -311,7 +319,8 @@ struct GatherArgs {
     int64_t *moffsets[DDSK_MAX_MULTI]; // optional per-variable [per_var + 1] byte offsets
     int min_seg_chunks;                // smallest segment, in chunks (claims cost more when the plan is in global memory)
     // ---- overlap protocol (DDS_OVERLAP: a batch declared independent of the ONE batch queued right before it)
-    //   * segments are strided statically (no shared ticket state);
+    //   * fixed-count launches stride their segments statically; variable-count launches (whose CTAs may start late,
+    //     behind the plan kernels) claim them by ticket from a word of their own slot, after passing the gate below;
     //   * launch q of a run may start while q-1 is still running (skip_wait: no griddepcontrol.wait), but
     //     - it does not write a byte of caller-visible memory before launch q-2 has RETIRED (gate on done[q-2]):
     //       a double-buffered queue that reuses the buffers of batch q-2 is safe whatever else occupies the GPU;
@@ -319,13 +328,20 @@ struct GatherArgs {
     //       the stream runs after launch q sees every earlier batch complete.
     //   Every CTA of q-2 and q-1 has started before the first CTA of q can (programmatic launch order), so the waits
     //   are on warps that are already running: no co-residency assumption, no deadlock.
-    //   * a variable-count launch planned by the plan kernels owns scratch slot q & 3; its lookup kernel skips the grid
-    //     wait too (so the PLAN of batch q runs under the gather of batch q-1) after checking that launch q-4, the
-    //     slot's previous user, has retired; the gather itself waits for its own plan kernels only.
+    //   * a variable-count launch planned by the plan kernels owns scratch slot q & 3. griddepcontrol.wait waits for
+    //     EVERY earlier grid of the stream (measured: with it, nothing of batch q moved before gather q-1 had finished),
+    //     so inside a run the two kernels of a batch are chained through memory instead: the plan kernel counts its
+    //     finished tiles and the last one publishes a plan-ready word (sequence number + packed total), the gather
+    //     spins on that word. The PLAN of batch q thus runs under the gather of batch q-1. The lookup kernel first checks that
+    //     launch q-4, the slot's previous user, has retired. A kernel only ever spins on kernels launched before it.
     int overlap, skip_wait;
     int wait1_valid, wait2_valid; // q-1 / q-2 belong to the same run
     unsigned int seq;             // q (per-store counter of overlap launches, wraps)
-    unsigned int *ovl;            // [0..3] finished-warp counters, [4..7] done words, slot = q & 3
+    unsigned int *ovl;            // per slot (q & 3): [0..3] finished-warp counters, [4..7] done words, [8..11] segment
+                                  // tickets, [12..15] plan tiles done
+    int wait_plan;                // the plan kernels of this launch signal through plan_word[slot] (no grid dependency)
+    unsigned long long *plan_word; // [4] per slot: (sequence number & 0xFFFFFF) << 40 | packed total, published by the scan kernel
+    unsigned int *tickets;        // the segment ticket word of this launch (counters[0], or ovl[8 + slot]); NULL: static striding
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
     unsigned long long *dbg;         // DDS_DEBUG_TIMING: per CTA [entry, plan done, first data, last warp done] (globaltimer ns)
 };
@@ -356,8 +372,9 @@ struct PlanView<0> {
     const uint64_t *src;
     const int64_t *dst;
     const uint32_t *seg_tab;
-    __device__ __forceinline__ uint64_t s(int64_t i) const { return src[i]; }
-    __device__ __forceinline__ int64_t d(int64_t i) const { return dst[i]; }
+    // (L2 loads: inside an overlap run the plan was written by kernels that ran concurrently with this one)
+    __device__ __forceinline__ uint64_t s(int64_t i) const { return __ldcg(&src[i]); }
+    __device__ __forceinline__ int64_t d(int64_t i) const { return __ldcg(&dst[i]); }
 };
 
 template <bool FIXED, int CH, int PCAP>
@@ -401,7 +418,7 @@ struct ChunkWalker {
     __device__ __forceinline__ int64_t locate_var(const GatherArgs &a, int64_t pos, int lane) {
         if (PCAP == 0) {
             // plan in global memory: the plan kernels left the answer for every SEG_GRAIN boundary (one load)
-            int64_t r0 = (int64_t)__ldg(&a.seg_tab[pos / SEG_GRAIN]);
+            int64_t r0 = (int64_t)__ldcg(&a.seg_tab[pos / SEG_GRAIN]);
             // zero-length requests right after it share its end offset only if pos is their start too; the table holds
             // the request whose bytes cover pos, which is the largest index with dst <= pos
             return r0;
@@ -430,12 +447,12 @@ struct ChunkWalker {
                 if (first_claim) {
                     first_claim = false;
                     seg = gwarp;
-                    if (!static_claims && seg < nseg && lane == 0) pend = atomicAdd(&a.counters[0], 1u);
+                    if (!static_claims && seg < nseg && lane == 0) pend = atomicAdd(a.tickets, 1u);
                 } else if (static_claims) {
                     seg = cur_seg + nwarps; // overlapped launches share no mutable state: plain striding
                 } else {
                     seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, pend, 0);
-                    if (seg < nseg && lane == 0) pend = atomicAdd(&a.counters[0], 1u);
+                    if (seg < nseg && lane == 0) pend = atomicAdd(a.tickets, 1u);
                 }
                 cur_seg = seg;
                 if (seg >= nseg) return 0;
@@ -704,7 +721,33 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             w.pv.src = a.req_src;
             w.pv.dst = a.req_dst;
             w.pv.seg_tab = a.seg_tab;
-            w.T = *(volatile const int64_t *)&a.req_dst[a.nreq];
+            if (a.wait_plan) {
+                // This batch's plan kernels publish through memory (they may still be running): one word carries
+                // "ready" and the packed total. Lane 1 checks the overlap gate (launch q-2 retired) in the same round
+                // trip, so a CTA that arrives in a running queue pays one L2 latency for both.
+                const bool need_gate = !gate_open;
+                unsigned long long pw = 0;
+                const uint64_t t0 = globaltimer_ns();
+                while (true) {
+                    bool ok = true;
+                    if (lane == 0) {
+                        pw = ld_acquire_u64(&a.plan_word[a.seq & 3u]);
+                        ok = (pw >> 40) == (unsigned long long)(a.seq & 0xFFFFFFu);
+                    } else if (lane == 1 && need_gate) {
+                        ok = (int)(ld_acquire_u32(&a.ovl[4 + ((a.seq - 2u) & 3u)]) - (a.seq - 2u)) >= 0;
+                    }
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    __nanosleep(100);
+                    if (globaltimer_ns() - t0 > 4000000000ull) {
+                        report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                        __trap();
+                    }
+                }
+                gate_open = true;
+                w.T = (int64_t)(__shfl_sync(0xffffffffu, pw, 0) & 0xFFFFFFFFFFull);
+            } else {
+                w.T = __ldcg(&a.req_dst[a.nreq]);
+            }
         }
     }
 
@@ -713,7 +756,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     // ---- total bytes, segment geometry -------------------------------------------------------
     w.gwarp = gwarp;
     w.nwarps = nwarps;
-    w.static_claims = a.overlap != 0;
+    w.static_claims = a.tickets == nullptr;
+    if (a.overlap && a.tickets) pass_gate(); // the slot's ticket word was last used by launch q-4
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     if (FIXED) w.T = w.nb * a.nreq;
     bool over = w.T > a.dst_cap;
@@ -881,6 +925,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             const unsigned int done = atomicAdd(&a.ovl[slot], 1u);
             if (done == (unsigned int)(nwarps - 1)) {
                 a.ovl[slot] = 0;
+                a.ovl[8 + slot] = 0;
                 if (a.wait1_valid) spin_until_done(a.ovl, a.seq - 1u, a.status, a.nreq);
                 __threadfence();
                 st_release_u32(&a.ovl[4 + slot], a.seq);
@@ -952,6 +997,15 @@ constexpr int PLAN_THREADS = 256;
 constexpr int PLAN_ITEMS = 4;
 constexpr int PLAN_TILE = PLAN_THREADS * PLAN_ITEMS;
 
+struct PlanProto { // overlap protocol as the plan kernel sees it (all zero: ordinary launch)
+    unsigned long long *dbg; // DDS_DEBUG_TIMING
+    unsigned int *ovl;
+    unsigned long long *plan_word;
+    int64_t *plan_total; // [4] per slot: the last tile parks the packed total here for whichever tile finishes last
+    unsigned int seq;
+    int skip_wait, wait2_valid, wait4_valid;
+};
+
 // block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, *total = block sum
 template <int NT>
 __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
@@ -972,83 +1026,126 @@ __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
     return base + inc - v;
 }
 
-// pass 1: per request source address + byte size (size parked in req_dst), per tile byte sum
-struct PlanProto { // overlap protocol as the plan kernels see it (all zero: ordinary launch)
-    const unsigned int *ovl;
-    unsigned int seq;
-    int skip_wait, wait2_valid, wait4_valid;
-};
+// The plan kernel: ONE pass. Every CTA takes a tile of PLAN_TILE requests (thread t: 4 consecutive ones), looks them up,
+// scans their sizes on chip, publishes the tile's byte count, resolves its offset by a decoupled look-back over the
+// tiles before it (words tagged with a per-launch tag, so no memset), and writes source addresses, packed offsets and
+// the segment table (which request covers every SEG_GRAIN boundary of the packed buffer -- a segment claim of the
+// gather is then one load instead of a search). The chain of DEPENDENT memory round trips is what this kernel costs
+// when it runs under the previous batch's gather (each one takes 2-3 us in a saturated memory system -- measured,
+// profiles/r2_queue_timeline.md), so there are as few as possible: index loads (+ the sample-table gather) and the
+// slot / gate polls in parallel, one look-back, one finish count.
+// tile_state word: [63:42] tag (22 bits) | [41:40] flag (1 = tile aggregate, 2 = inclusive prefix) | [39:0] bytes
+__device__ __forceinline__ unsigned long long tile_pack(unsigned int tag, unsigned int flag, int64_t v) {
+    return ((unsigned long long)(tag & 0x3FFFFFu) << 42) | ((unsigned long long)flag << 40) |
+           ((unsigned long long)v & 0xFFFFFFFFFFull);
+}
 
-__global__ void __launch_bounds__(PLAN_THREADS) dds_plan_lookup_kernel(const __grid_constant__ ddsk_var_t var,
-                                                                       const __grid_constant__ PlanSrc p, int64_t nreq,
-                                                                       uint64_t *__restrict__ req_src,
-                                                                       int64_t *__restrict__ req_dst,
-                                                                       int64_t *__restrict__ tile_sums,
-                                                                       unsigned long long *status, PlanProto pr) {
+__global__ void __launch_bounds__(PLAN_THREADS) dds_plan_kernel(const __grid_constant__ ddsk_var_t var,
+                                                                const __grid_constant__ PlanSrc p, int64_t nreq,
+                                                                uint64_t *__restrict__ req_src, int64_t *__restrict__ req_dst,
+                                                                unsigned long long *tile_state, unsigned int tag,
+                                                                int64_t *__restrict__ offsets_out, uint32_t *__restrict__ seg_tab,
+                                                                int64_t seg_cap, unsigned long long *status, PlanProto pr) {
+    __shared__ int64_t warp_tot[PLAN_THREADS / 32];
+    __shared__ int64_t tile_excl_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (pr.dbg && threadIdx.x == 0) atomicMax(&pr.dbg[4096 + 0], (unsigned long long)globaltimer_ns());
     if (!pr.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (pr.wait4_valid) { // the scratch slot's previous user (launch seq-4) must have retired before it is overwritten
-        if (threadIdx.x == 0) spin_until_done(pr.ovl, pr.seq - 4u, status, nreq);
-        __syncthreads();
-    }
-    const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
+    // tiles are taken in launch order (blockIdx); a tile only ever waits for lower-numbered tiles
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * PLAN_TILE + (int64_t)threadIdx.x * PLAN_ITEMS;
     int64_t idx[PLAN_ITEMS], nb[PLAN_ITEMS];
     uint64_t sv[PLAN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < PLAN_ITEMS; k++) idx[k] = base + (int64_t)k * PLAN_THREADS + threadIdx.x; // striped
-    plan_many<PLAN_ITEMS>(var, p, idx, nreq, status, sv, nb);
+    for (int k = 0; k < PLAN_ITEMS; k++) idx[k] = base + k;
+    plan_many<PLAN_ITEMS>(var, p, idx, nreq, status, sv, nb); // (only reads: may run before the slot is known to be free)
     int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_ITEMS; k++) mine += nb[k];
+    const int64_t incl = warp_incl_scan(mine, lane);
+    if (lane == 31) warp_tot[wid] = incl;
+    // the scratch slot's previous user (launch seq-4) must have retired before anything is written to the slot; the
+    // offsets are caller-visible, so launch seq-2 must have retired too (it implies seq-4): one poll, issued with the
+    // index loads above in flight
+    if (threadIdx.x == 0) {
+        if (pr.wait2_valid && offsets_out) spin_until_done(pr.ovl, pr.seq - 2u, status, nreq);
+        else if (pr.wait4_valid) spin_until_done(pr.ovl, pr.seq - 4u, status, nreq);
+    }
+    __syncthreads();
+    int64_t wbase = 0, agg = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_THREADS / 32; k++) {
+        const int64_t t = warp_tot[k];
+        if (k < wid) wbase += t;
+        agg += t;
+    }
+    // ---- publish the aggregate, look back
+    if (wid == 0) {
+        if (lane == 0) st_release_u64(&tile_state[tile], tile_pack(tag, tile == 0 ? 2u : 1u, agg));
+        int64_t excl = 0;
+        if (tile > 0) {
+            int64_t win = tile - 1;
+            const uint64_t t0 = globaltimer_ns();
+            while (true) {
+                const int64_t t = win - lane; // lane 0 polls the nearest predecessor
+                unsigned long long wv = tile_pack(tag, 2u, 0);
+                if (t >= 0) {
+                    do {
+                        wv = ld_acquire_u64(&tile_state[t]);
+                        if (globaltimer_ns() - t0 > 4000000000ull) { // never expected; do not hang the box
+                            report(status, nreq, DDSK_CODE_WATCHDOG);
+                            __trap();
+                        }
+                    } while ((unsigned int)(wv >> 42) != (tag & 0x3FFFFFu) || ((wv >> 40) & 3u) == 0);
+                }
+                const unsigned int flag = (unsigned int)((wv >> 40) & 3u);
+                const int64_t val = (int64_t)(wv & 0xFFFFFFFFFFull);
+                const unsigned inc = __ballot_sync(0xffffffffu, flag == 2u);
+                const int stop = inc ? __ffs(inc) - 1 : 31; // nearest tile that already knows its inclusive prefix
+                excl += warp_sum(lane <= stop ? val : 0);
+                if (inc) break;
+                win -= 32;
+            }
+            if (lane == 0) st_release_u64(&tile_state[tile], tile_pack(tag, 2u, excl + agg));
+        }
+        if (lane == 0) tile_excl_s = excl;
+    }
+    __syncthreads();
+    int64_t run = tile_excl_s + wbase + incl - mine;
 #pragma unroll
     for (int k = 0; k < PLAN_ITEMS; k++) {
         if (idx[k] < nreq) {
+            const int64_t d0 = run, d1 = run + nb[k];
             req_src[idx[k]] = sv[k];
-            req_dst[idx[k]] = nb[k];
-            mine += nb[k];
+            req_dst[idx[k]] = d0;
+            if (offsets_out) offsets_out[idx[k]] = d0;
+            for (int64_t g = (d0 + SEG_GRAIN - 1) / SEG_GRAIN; g * SEG_GRAIN < d1 && g < seg_cap; g++) seg_tab[g] = (uint32_t)idx[k];
+            run = d1;
         }
     }
-    int64_t tot;
-    block_excl_scan<PLAN_THREADS>(mine, &tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-}
-
-// pass 2: exclusive scan. Each CTA sums the tiles before it, then scans its own tile in place, and notes in the
-// segment table which request covers every SEG_GRAIN boundary of the packed buffer that falls inside its requests
-// (so a segment claim of the gather is one load instead of a search over req_dst).
-__global__ void __launch_bounds__(PLAN_THREADS) dds_plan_scan_kernel(int64_t nreq, int64_t *__restrict__ req_dst,
-                                                                     const int64_t *__restrict__ tile_sums,
-                                                                     int64_t *__restrict__ offsets_out,
-                                                                     uint32_t *__restrict__ seg_tab, int64_t seg_cap,
-                                                                     unsigned long long *status, PlanProto pr) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory"); // the lookup kernel of this batch
-    if (pr.wait2_valid && offsets_out) { // offsets are caller-visible: not before launch seq-2 has retired
-        if (threadIdx.x == 0) spin_until_done(pr.ovl, pr.seq - 2u, status, nreq);
+    const bool last_tile = tile == (int64_t)gridDim.x - 1;
+    const int64_t T = tile_excl_s + agg;
+    if (last_tile && threadIdx.x == 0) {
+        req_dst[nreq] = T;
+        if (offsets_out) offsets_out[nreq] = T;
+    }
+    if (pr.dbg && threadIdx.x == 0) atomicMax(&pr.dbg[4096 + 1], (unsigned long long)globaltimer_ns());
+    if (pr.ovl) { // overlap run: the gather of this batch spins on the plan word instead of waiting for the grid. The
+                  // last tile to finish re-arms the count and publishes "ready" + the packed total.
         __syncthreads();
-    }
-    int64_t part = 0;
-    for (int64_t t = threadIdx.x; t < (int64_t)blockIdx.x; t += PLAN_THREADS) part += tile_sums[t];
-    int64_t tile_base;
-    block_excl_scan<PLAN_THREADS>(part, &tile_base);
-    // layout inside a tile is striped (item k of thread t = k*THREADS + t): scan stripe by stripe
-    const int64_t base = (int64_t)blockIdx.x * PLAN_TILE;
-    int64_t running = tile_base;
-#pragma unroll
-    for (int k = 0; k < PLAN_ITEMS; k++) {
-        int64_t i = base + (int64_t)k * PLAN_THREADS + threadIdx.x;
-        int64_t v = i < nreq ? req_dst[i] : 0;
-        int64_t tot;
-        int64_t ex = block_excl_scan<PLAN_THREADS>(v, &tot);
-        if (i < nreq) {
-            const int64_t d0 = running + ex, d1 = d0 + v;
-            req_dst[i] = d0;
-            if (offsets_out) offsets_out[i] = d0;
-            for (int64_t g = (d0 + SEG_GRAIN - 1) / SEG_GRAIN; g * SEG_GRAIN < d1 && g < seg_cap; g++) seg_tab[g] = (uint32_t)i;
+        if (threadIdx.x == 0) {
+            const unsigned int slot = pr.seq & 3u;
+            if (last_tile) *(volatile int64_t *)&pr.plan_total[slot] = T;
+            __threadfence();
+            if (atomicAdd(&pr.ovl[12 + slot], 1u) == gridDim.x - 1) {
+                pr.ovl[12 + slot] = 0;
+                __threadfence();
+                const unsigned long long Tw = (unsigned long long)*(volatile int64_t *)&pr.plan_total[slot];
+                __threadfence();
+                st_release_u64(&pr.plan_word[slot], ((unsigned long long)(pr.seq & 0xFFFFFFu) << 40) | (Tw & 0xFFFFFFFFFFull));
+            }
         }
-        running += tot;
-    }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-        req_dst[nreq] = running;
-        if (offsets_out) offsets_out[nreq] = running;
     }
 }
 
@@ -1098,6 +1195,87 @@ __global__ void dds_verify_kernel(const __grid_constant__ ddsk_var_t var, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dds_doorbell_kernel: the same single request WITHOUT a kernel launch. One CTA stays resident for as long as get()
+// calls keep coming (it leaves by itself after `idle_ns` without one, so a device-wide synchronize never waits longer
+// than that) and polls a mailbox in mapped pinned host memory: the host writes the request fields, then a sequence
+// number; the kernel does the reference's checks, copies the rows (to device memory, or zero-copy to a pinned bounce
+// buffer) and answers with ONE word, (sequence << 8) | code. A launch + completion costs ~14 us on this box, a
+// mailbox round trip ~5 (measured: profiles/r2_latency.md).
+// Exit protocol: the kernel's last action is to write its generation number to mb->exit_gen; it never touches the
+// mailbox afterwards. A host that finds exit_gen == the generation it believes alive while its request is still
+// unanswered launches a fresh kernel (which starts by looking for an unserved request), so no request is lost or
+// served twice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dds_doorbell_kernel(const ddsk_var_t *__restrict__ vars, ddsk_mailbox_t *mb,
+                                                           unsigned long long served, unsigned long long gen,
+                                                           unsigned long long idle_ns) {
+    // the request of the current round: [0] seq_head [1] start [2] count [3] dst [4] dst_cap [5] var | stop << 32 [7] seq_tail
+    __shared__ unsigned long long req[8];
+    __shared__ int sh_state; // 0: serve req[], 1: leave (idle), 2: leave (asked to)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (true) {
+        if (warp == 0) {
+            // Only this warp polls; the other warps sleep in the barrier below. One poll = ONE coalesced 64-byte read of
+            // the request line over PCIe (lanes 0..7, 8 bytes each). The host writes the fields, then seq_tail, then
+            // seq_head; a request counts as posted when BOTH equal a new sequence number, which makes the snapshot
+            // consistent whatever order the line's pieces are fetched in.
+            const uint64_t t0 = globaltimer_ns();
+            int state = -1;
+            while (state < 0) {
+                unsigned long long w = 0;
+                if (lane < 8) w = ((volatile unsigned long long *)mb)[lane];
+                const unsigned long long head = __shfl_sync(0xffffffffu, w, 0), tail = __shfl_sync(0xffffffffu, w, 7);
+                if (head != served && head == tail) {
+                    if (lane < 8) req[lane] = w;
+                    state = (int)((__shfl_sync(0xffffffffu, w, 5) >> 32) & 1ull) ? 2 : 0;
+                } else if (globaltimer_ns() - t0 > idle_ns) {
+                    state = 1;
+                }
+            }
+            if (lane == 0) sh_state = state;
+        }
+        __syncthreads();
+        const int state = sh_state;
+        const unsigned long long q = req[0];
+        if (state != 0) { // idle for too long, or asked to leave (that request IS the stop: answer it, then go)
+            if (threadIdx.x == 0) {
+                if (state == 2) {
+                    *(volatile unsigned long long *)&mb->resp = (q << 8);
+                    __threadfence_system();
+                }
+                *(volatile unsigned long long *)&mb->exit_gen = gen;
+                __threadfence_system();
+            }
+            return;
+        }
+        const int64_t start = (int64_t)req[1], count = (int64_t)req[2], cap = (int64_t)req[4];
+        char *dp = (char *)req[3];
+        const ddsk_var_t &var = vars[(int)(req[5] & 0xFFFFFFFFull)];
+        uint64_t src = 0;
+        const int code = dev_locate(var, start, count, &src);
+        const int64_t n = code ? 0 : count * var.row_bytes;
+        unsigned long long st = 0; // 0 = ok in the mailbox encoding
+        if (code) st = (unsigned long long)code;
+        else if (n > cap) st = DDSK_CODE_CAPACITY;
+        if (st == 0 && n > 0) {
+            const char *sp = (const char *)src;
+            if ((((uint64_t)sp | (uint64_t)dp | (uint64_t)n) & 15u) == 0) {
+                for (int64_t i = threadIdx.x; i < (n >> 4); i += blockDim.x) ((uint4 *)dp)[i] = ((const uint4 *)sp)[i];
+            } else if ((((uint64_t)sp | (uint64_t)dp | (uint64_t)n) & 3u) == 0) {
+                for (int64_t i = threadIdx.x; i < (n >> 2); i += blockDim.x) ((uint32_t *)dp)[i] = ((const uint32_t *)sp)[i];
+            } else {
+                for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dp[i] = sp[i];
+            }
+            __threadfence_system(); // the payload is visible (host memory or HBM) before the answer is
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *(volatile unsigned long long *)&mb->resp = (q << 8) | st;
+        served = q;
+        // (the next poll overwrites req[]: every thread has read it before the barrier above)
+    }
+}
+
 // Test helper: hold `gridDim.x` SMs' worth of shared memory busy for `ns` nanoseconds (a stand-in for a training kernel
 // that shares the GPU with a prefetch queue; tests/test_gpu_parity.py uses it to attack the overlap protocol).
 __global__ void dds_occupy_kernel(unsigned long long ns) {
@@ -1115,7 +1293,9 @@ struct Geometry {
     int nw, stages, ch, pcap;
 };
 // plan-in-global variants (fixed-count entry, and variable-count batches above 8192 requests)
-constexpr Geometry kGeoms[] = {{8, 4, 4096, 0}, {8, 6, 4096, 0}, {16, 3, 4096, 0}, {4, 4, 8192, 0}, {12, 4, 4096, 0}, {4, 6, 4096, 0}};
+constexpr Geometry kGeoms[] = {{8, 4, 4096, 0}, {8, 6, 4096, 0}, {16, 3, 4096, 0}, {4, 4, 8192, 0}, {12, 4, 4096, 0}, {4, 6, 4096, 0},
+                               {6, 4, 4096, 0},   // (5-6: half-size CTAs, two per SM with DDS_GATHER_CTAS_PER_SM=2)
+                               {12, 3, 4096, 0}}; // (7: less in flight per SM -> shorter memory queues)
 constexpr int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 // plan-in-shared-memory variants (variable-count entry): the plan's 12 B per request come out of the stage budget
 constexpr Geometry kGeomsS[] = {{12, 3, 4096, 4096}, {12, 3, 3072, 8192}, {16, 3, 2048, 8192}, {16, 3, 3072, 4096}, {8, 4, 4096, 4096}};
@@ -1138,7 +1318,12 @@ bool g_geom_init = false;
 int g_sms = 0;
 int g_ctas_per_sm = 1;
 int g_pdl = 1;
-unsigned long long *g_dbg = nullptr; // DDS_DEBUG_TIMING=1: device buffer of per-CTA timestamps of the LAST gather launch
+// DDS_DEBUG_TIMING=1: device buffer of globaltimer stamps, two regions (overlap launches alternate by sequence parity):
+// [cta * 4 + {entry, plan known, first data, last warp done}] for cta < 1024, then [4096 + {lookup last CTA start, lookup
+// last CTA end, scan last CTA start, scan last CTA end}]. Never reset (every stamp only grows).
+unsigned long long *g_dbg = nullptr;
+constexpr size_t kDbgRegion = 4096 + 8;
+int g_plan_carveout = 1; // DDS_PLAN_CARVEOUT: plan kernels ask for the gather's shared-memory carve-out (A/B switch)
 int g_smem_plan = 1; // DDS_SMEM_PLAN: 1 = plan in shared memory when it fits (default), 0 = always the plan kernels (A/B switch)
 
 int pick_geometry() {
@@ -1159,10 +1344,11 @@ int pick_geometry() {
     if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
     if (const char *e = getenv("DDS_SMEM_PLAN")) g_smem_plan = atoi(e);
     if (const char *e = getenv("DDS_SMEM_PLAN_MAX")) g_plan_smem_default = atoll(e);
+    if (const char *e = getenv("DDS_PLAN_CARVEOUT")) g_plan_carveout = atoi(e);
     if (const char *e = getenv("DDS_DEBUG_TIMING"))
         if (atoi(e)) {
-            CUDA_TRY(cudaMalloc((void **)&g_dbg, 1024 * 4 * 8));
-            CUDA_TRY(cudaMemset(g_dbg, 0, 1024 * 4 * 8));
+            CUDA_TRY(cudaMalloc((void **)&g_dbg, 2 * kDbgRegion * 8));
+            CUDA_TRY(cudaMemset(g_dbg, 0, 2 * kDbgRegion * 8));
         }
     g_geom_init = true;
     return 0;
@@ -1203,8 +1389,7 @@ int launch_gather_t(const GatherArgs &args_in, cudaStream_t stream) {
     }
     const int per_sm = ctas_per_sm_for(NW, S, CH, PCAP);
     GatherArgs args = args_in;
-    args.dbg = g_dbg;
-    if (g_dbg) CUDA_TRY(cudaMemsetAsync(g_dbg, 0, 1024 * 4 * 8, stream));
+    args.dbg = g_dbg ? g_dbg + (size_t)(args.overlap ? (args.seq & 1u) : 0u) * kDbgRegion : nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(g_sms * per_sm));
     cfg.blockDim = dim3(NW * 32);
@@ -1223,6 +1408,15 @@ int launch_gather_t(const GatherArgs &args_in, cudaStream_t stream) {
 // launch with the programmatic-dependent-launch attribute (the kernels call griddepcontrol.wait themselves)
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    // The plan kernels are meant to run on SMs that a gather CTA (max shared-memory carve-out) still occupies: ask for
+    // the same carve-out, or the SM would have to drain before it can host them.
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (g_plan_carveout && (dev >= 64 || !(configured.load() & (1ull << dev)))) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        if (dev < 64) configured.fetch_or(1ull << dev);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -1246,6 +1440,8 @@ int launch_gather(const GatherArgs &args, cudaStream_t stream) {
     case 3: return launch_gather_t<FIXED, 4, 4, 8192, 0>(args, stream);
     case 4: return launch_gather_t<FIXED, 12, 4, 4096, 0>(args, stream);
     case 5: return launch_gather_t<FIXED, 4, 6, 4096, 0>(args, stream);
+    case 6: return launch_gather_t<FIXED, 6, 4, 4096, 0>(args, stream);
+    case 7: return launch_gather_t<FIXED, 12, 3, 4096, 0>(args, stream);
     default: return launch_gather_t<FIXED, 8, 4, 4096, 0>(args, stream);
     }
 }
@@ -1266,6 +1462,7 @@ void fill_overlap(GatherArgs &a, const ddsk_scratch_t *scr, int flags) {
     a.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
     a.seq = scr->ovl_seq;
     a.ovl = scr->ovl;
+    a.tickets = a.overlap ? nullptr : scr->counters;
 }
 
 } // namespace
@@ -1278,11 +1475,11 @@ extern "C" {
 const char *ddsk_last_cuda_error(void) { return g_cuda_err; }
 unsigned long long ddsk_launch_count(void) { return g_launches.load(); }
 int64_t ddsk_plan_smem_max(void) { return kPlanSmemMax; }
-int ddsk_debug_timing(unsigned long long *host_out, int max_ctas) { // [cta][4] of the last gather launch; returns CTAs
+int ddsk_debug_timing(unsigned long long *host_out, int max_words) { // both regions, 2 * (4096 + 8) words
     if (!g_dbg) return 0;
-    const int n = max_ctas < 1024 ? max_ctas : 1024;
-    if (cudaMemcpy(host_out, g_dbg, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return n;
+    const size_t n = (size_t)max_words < 2 * kDbgRegion ? (size_t)max_words : 2 * kDbgRegion;
+    if (cudaMemcpy(host_out, g_dbg, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)n;
 }
 
 void ddsk_gather_geometry(int *ctas, int *warps_per_cta, int *stages, int *chunk_bytes, int *smem_bytes) {
@@ -1336,6 +1533,7 @@ static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq
         a.offsets_out = offsets_dev_or_null;
         a.min_seg_chunks = g_min_seg_s;
         fill_overlap(a, scr, flags); // no scratch is shared between launches: independent batches may overlap
+        if (a.overlap) a.tickets = scr->ovl + 8 + (a.seq & 3u);
         return launch_gather_s(gs, a, st);
     }
     if (nreq > scr->cap_req || cap_total / SEG_GRAIN + 2 > scr->seg_cap) {
@@ -1348,18 +1546,22 @@ static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq
     PlanProto pr;
     memset(&pr, 0, sizeof(pr));
     if (flags & DDSK_F_OVERLAP) {
+        pr.dbg = g_dbg ? g_dbg + (size_t)(scr->ovl_seq & 1u) * kDbgRegion : nullptr;
         pr.ovl = scr->ovl;
+        pr.plan_word = scr->plan_word;
+        pr.plan_total = (int64_t *)(scr->plan_word + 4);
         pr.seq = scr->ovl_seq;
         pr.skip_wait = (flags & DDSK_F_SKIP_WAIT) ? 1 : 0;
         pr.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
         pr.wait4_valid = (flags & DDSK_F_PREV4) ? 1 : 0;
     }
     const int tiles = (int)((nreq + PLAN_TILE - 1) / PLAN_TILE);
-    if (int rc = launch_pdl(dds_plan_lookup_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq, scr->req_src,
-                            scr->req_dst, scr->tile_sums, scr->status, pr))
-        return rc;
-    if (int rc = launch_pdl(dds_plan_scan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, nreq, scr->req_dst,
-                            (const int64_t *)scr->tile_sums, offsets_dev_or_null, scr->seg_tab, scr->seg_cap, scr->status, pr))
+    // tags the look-back words of this launch (they are never cleared; the caller clears every scratch area it owns
+    // when the 22-bit tag is about to wrap and restarts it at 0)
+    scr->plan_tag = (scr->plan_tag + 1) & 0x3FFFFFu;
+    if (int rc = launch_pdl(dds_plan_kernel, dim3(tiles), dim3(PLAN_THREADS), st, *var, p, nreq, scr->req_src, scr->req_dst,
+                            (unsigned long long *)scr->tile_sums, scr->plan_tag, offsets_dev_or_null, scr->seg_tab, scr->seg_cap,
+                            scr->status, pr))
         return rc;
     a.req_src = scr->req_src;
     a.req_dst = scr->req_dst;
@@ -1367,7 +1569,11 @@ static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq
     a.total_out = nullptr;
     a.min_seg_chunks = g_min_seg_var;
     fill_overlap(a, scr, flags);
-    a.skip_wait = 0; // the gather always waits for its own plan kernels (which finished long ago in a running queue)
+    if (a.overlap) {
+        a.tickets = scr->ovl + 8 + (a.seq & 3u);
+        a.wait_plan = 1; // (a.skip_wait: inside a run the gather skips the grid wait and spins on the plan-ready word)
+        a.plan_word = scr->plan_word;
+    }
     return launch_gather<false>(a, st);
 }
 
@@ -1437,6 +1643,14 @@ int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int6
 int ddsk_small_get(const ddsk_var_t *var, int64_t start, int64_t count, void *dst, int64_t dst_capacity,
                    unsigned long long *flag_dev, unsigned long long ticket, void *stream) {
     dds_small_get_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*var, start, count, (char *)dst, dst_capacity, flag_dev, ticket);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ddsk_doorbell_launch(const ddsk_var_t *vars_dev, ddsk_mailbox_t *mailbox_dev, unsigned long long served,
+                         unsigned long long gen, unsigned long long idle_ns, void *stream) {
+    dds_doorbell_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(vars_dev, mailbox_dev, served, gen, idle_ns);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;

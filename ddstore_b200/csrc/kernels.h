@@ -37,12 +37,17 @@ typedef struct ddsk_scratch {
     unsigned long long *status; /* 1 word, sticky (kernels only atomicMin into it) */
     int64_t *total;             /* 1 word: packed total of the last variable-count launch planned in shared memory */
     unsigned int *counters;     /* 2 words: [0] segment ticket, [1] finished warps -- self-resetting */
-    unsigned int *ovl;          /* 8 words of the overlap protocol: [0..3] finished-warp counters, [4..7] done words */
+    unsigned int *ovl;          /* 24 words of the overlap protocol, one of each kind per slot (sequence number & 3):
+                                   finished-warp counters, done words, segment tickets, lookup tiles done, scan tiles
+                                   done, plan-ready words */
+    unsigned long long *plan_word; /* 8 words: [0..3] per slot (sequence number & 0xFFFFFF) << 40 | packed total ("plan
+                                      ready"), [4..7] per slot the packed total parked by the plan kernel's last tile */
     unsigned int ovl_seq;       /* sequence number the NEXT overlap launch carries (host side, set by the caller) */
     /* plan in global memory (variable-count batches above ddsk_plan_smem_max() requests, or >= 4 GiB destinations) */
     uint64_t *req_src;          /* [cap_req]   planned source address per request (0 = skip) */
     int64_t *req_dst;           /* [cap_req+1] exclusive scan of request bytes */
-    int64_t *tile_sums;         /* [cap_req/1024 + 2] tile sums of the plan kernels */
+    int64_t *tile_sums;         /* [cap_req/1024 + 2] look-back words of the plan kernel (tagged per launch, never cleared) */
+    unsigned int plan_tag;      /* host-side launch counter tagging them (22 bits; 0 = never used) */
     int64_t cap_req;
     uint32_t *seg_tab;          /* [seg_cap] request covering byte k * 16384 of the packed buffer */
     int64_t seg_cap;
@@ -109,6 +114,28 @@ int ddsk_small_get(const ddsk_var_t *var, int64_t start, int64_t count, void *ds
  * splitmix64(seed ^ (g*disp + c)). Bench / test helper, fills a local shard in place. */
 int ddsk_synth_fill(void *base_dev, int64_t first_global_row, int64_t nrows, int64_t disp, int itemsize, uint64_t seed,
                     void *stream);
+
+/* Mailbox of the doorbell kernel (mapped pinned host memory; request line written by the host, answer line by the
+ * device). resp = (req_seq << 8) | code, code 0 = ok, else DDSK_CODE_*; exit_gen = generation of the kernel that left. */
+typedef struct ddsk_mailbox {
+    /* request line (64 bytes, read by the device in one piece): the host writes the fields, then seq_tail, then seq_head */
+    unsigned long long seq_head;
+    int64_t start, count;
+    uint64_t dst;
+    int64_t dst_cap;
+    uint64_t var_stop; /* low 32 bits: index into the device table of windows; bit 32: this request asks the kernel to leave */
+    unsigned long long pad0_;
+    unsigned long long seq_tail;
+    unsigned long long pad_[8];
+    /* answer line (written by the device) */
+    unsigned long long resp;
+    unsigned long long exit_gen;
+    unsigned long long pad2_[14];
+} ddsk_mailbox_t;
+/* One resident CTA serving single-row requests from the mailbox until idle for idle_ns; `served` = last sequence number
+ * already answered, `gen` = this kernel's generation (written to exit_gen when it leaves). */
+int ddsk_doorbell_launch(const ddsk_var_t *vars_dev, ddsk_mailbox_t *mailbox_dev, unsigned long long served,
+                         unsigned long long gen, unsigned long long idle_ns, void *stream);
 
 /* Check a packed batch against the generator on the device: request i = rows [starts[i], +counts[i] or fixed_count) at
  * byte offset offsets[i] (or i * fixed_count * disp * itemsize). out_dev: 2 + DDSK_MAX_RANKS words, accumulated into:

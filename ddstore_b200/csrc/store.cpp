@@ -12,11 +12,15 @@
 // All CUDA work goes through the CUDA runtime C API and the ddsk_* launchers (kernels.h).
 // There is no CPU data path: if no device is usable, dds_create fails with DDS_ERR_NO_DEVICE.
 #include <cuda_runtime_api.h>
+#include <sched.h>
 #include <sys/random.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -122,6 +126,7 @@ struct Var {
     std::vector<dds_vmm::Block> peer_block;
     bool fence_active = false;
     ddsk_var_t kv;
+    int id = -1; // slot of kv in the store's device table of windows (doorbell kernel); -1: not there
     // per-sample index: sample i owns rows [tab_start[i], tab_start[i] + tab_count[i])
     int64_t *d_tab = nullptr; // [nsamples][2] = {row_start, row_count}: one 16-byte load per sample id
     int64_t nsamples = 0;
@@ -129,6 +134,69 @@ struct Var {
 };
 
 } // namespace
+
+// Streaming ingest: a few worker threads copy slices of a pageable source chunk into a pinned
+// staging buffer in parallel (one thread's memcpy tops out around 12-15 GB/s, a PCIe Gen5 x16 link wants ~55), while
+// the copy engine moves the previous staging buffer into the shard.
+struct IngestPool {
+    static constexpr size_t kStage = 16u << 20; // bytes per staging buffer
+    char *pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ev_pending[2] = {false, false};
+    cudaStream_t stream = nullptr;
+    int next = 0;
+    // fork-join pool
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    unsigned long long gen = 0;
+    int remaining = 0;
+    bool quit = false;
+    const char *src = nullptr;
+    char *dst = nullptr;
+    size_t bytes = 0;
+
+    void worker(int idx, int n) {
+        unsigned long long seen = 0;
+        while (true) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return quit || gen != seen; });
+            if (quit) return;
+            seen = gen;
+            const char *sp = src;
+            char *dp = dst;
+            const size_t total = bytes;
+            lk.unlock();
+            const size_t per = ((total + n - 1) / n + 4095) & ~(size_t)4095;
+            const size_t lo = std::min(total, per * (size_t)idx), hi = std::min(total, lo + per);
+            if (hi > lo) memcpy(dp + lo, sp + lo, hi - lo);
+            lk.lock();
+            if (--remaining == 0) cv_done.notify_one();
+        }
+    }
+    void start(int n) {
+        for (int i = 0; i < n; i++) workers.emplace_back([this, i, n] { worker(i, n); });
+    }
+    void copy(char *d, const char *sp, size_t n) { // all workers copy their slice of [sp, sp + n) to d; returns when done
+        std::unique_lock<std::mutex> lk(mu);
+        src = sp;
+        dst = d;
+        bytes = n;
+        remaining = (int)workers.size();
+        gen++;
+        cv_go.notify_all();
+        cv_done.wait(lk, [&] { return remaining == 0; });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv_go.notify_all();
+        for (auto &t : workers) t.join();
+        workers.clear();
+    }
+};
 
 struct dds_store {
     dds_comm_t *comm = nullptr;
@@ -172,7 +240,16 @@ struct dds_store {
     int64_t *d_offs = nullptr; // device staging of byte offsets (host destinations, multi-array totals)
     int64_t offs_cap = 0;
     unsigned long long small_ticket = 0; // ticket of the last dds_small_get launch
+    // doorbell (launch-free single-request path): a mailbox in mapped pinned memory and one resident CTA polling it
+    static constexpr int kMaxDbVars = 256;
+    ddsk_mailbox_t *h_mb = nullptr, *d_mb = nullptr;
+    cudaStream_t db_stream = nullptr;
+    ddsk_var_t *d_vars = nullptr;
+    int next_var_id = 0;
+    unsigned long long db_seq = 0, db_gen = 0, db_idle_ns = 200000;
+    bool db_alive = false, db_enabled = true;
     std::set<cudaStream_t> update_streams; // caller streams that carried dds_update_async copies since the last fence
+    IngestPool *ingest = nullptr;
 };
 
 namespace {
@@ -185,12 +262,42 @@ uint64_t host_tag() {
     return h;
 }
 
+// ---- doorbell kernel lifecycle
+// ask the resident CTA (if any) to leave and wait until it has: needed before anything that synchronises the device
+int db_stop(dds_store *s) {
+    if (!s->db_alive) return DDS_OK;
+    volatile ddsk_mailbox_t *mb = s->h_mb;
+    if (mb->exit_gen != s->db_gen) {
+        mb->var_stop = 1ull << 32;
+        std::atomic_thread_fence(std::memory_order_release);
+        const unsigned long long q = ++s->db_seq;
+        mb->seq_tail = q;
+        std::atomic_thread_fence(std::memory_order_release);
+        mb->seq_head = q;
+        for (unsigned spins = 0; mb->exit_gen != s->db_gen; spins++) {
+            if ((spins & 0xFFFF) == 0xFFFF && cudaStreamQuery(s->db_stream) != cudaErrorNotReady) break;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    s->db_alive = false;
+    cudaError_t e = cudaStreamSynchronize(s->db_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "doorbell kernel");
+    return DDS_OK;
+}
+
+cudaError_t device_sync(dds_store *s) {
+    db_stop(s);
+    return cudaDeviceSynchronize();
+}
+
 // scratch of the plan kernels (variable-count batches the shared-memory plan does not take)
 int ensure_scratch(dds_store *s, int64_t nreq, int64_t cap_bytes) {
     if (nreq > s->scr.cap_req) {
         int64_t cap = std::max<int64_t>(16384, s->scr.cap_req);
         while (cap < nreq) cap *= 2;
-        CU(cudaDeviceSynchronize()); // nothing queued may still be reading the old arrays
+        CU(device_sync(s)); // nothing queued may still be reading the old arrays
         if (s->scr.req_src) cudaFree(s->scr.req_src);
         if (s->scr.req_dst) cudaFree(s->scr.req_dst);
         if (s->scr.tile_sums) cudaFree(s->scr.tile_sums);
@@ -201,13 +308,14 @@ int ensure_scratch(dds_store *s, int64_t nreq, int64_t cap_bytes) {
         CU(cudaMalloc((void **)&s->scr.req_src, (size_t)cap * 8));
         CU(cudaMalloc((void **)&s->scr.req_dst, (size_t)(cap + 1) * 8));
         CU(cudaMalloc((void **)&s->scr.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+        CU(cudaMemset(s->scr.tile_sums, 0, (size_t)(cap / 1024 + 2) * 8));
         s->scr.cap_req = cap;
     }
     const int64_t need = cap_bytes / 16384 + 2; // one entry per SEG_GRAIN of the packed buffer
     if (need > s->scr.seg_cap) {
         int64_t cap = std::max<int64_t>(1 << 16, s->scr.seg_cap);
         while (cap < need) cap *= 2;
-        CU(cudaDeviceSynchronize());
+        CU(device_sync(s));
         if (s->scr.seg_tab) cudaFree(s->scr.seg_tab);
         s->scr.seg_tab = nullptr;
         s->scr.seg_cap = 0;
@@ -223,7 +331,7 @@ int ensure_slots(dds_store *s, int64_t nreq, int64_t cap_bytes) {
     int64_t cap = std::max<int64_t>(16384, s->slots[0].cap_req), scap = std::max<int64_t>(1 << 16, s->slots[0].seg_cap);
     while (cap < nreq) cap *= 2;
     while (scap < need_seg) scap *= 2;
-    CU(cudaDeviceSynchronize()); // nothing queued may still be using the old slots
+    CU(device_sync(s)); // nothing queued may still be using the old slots
     s->run_len = 0;              // ... so the next overlap launch starts a new run
     for (auto &sl : s->slots) {
         if (sl.req_src) cudaFree(sl.req_src);
@@ -234,6 +342,7 @@ int ensure_slots(dds_store *s, int64_t nreq, int64_t cap_bytes) {
         CU(cudaMalloc((void **)&sl.req_src, (size_t)cap * 8));
         CU(cudaMalloc((void **)&sl.req_dst, (size_t)(cap + 1) * 8));
         CU(cudaMalloc((void **)&sl.tile_sums, (size_t)(cap / 1024 + 2) * 8));
+        CU(cudaMemset(sl.tile_sums, 0, (size_t)(cap / 1024 + 2) * 8));
         CU(cudaMalloc((void **)&sl.seg_tab, (size_t)scap * 4));
         sl.cap_req = cap;
         sl.seg_cap = scap;
@@ -243,6 +352,19 @@ int ensure_slots(dds_store *s, int64_t nreq, int64_t cap_bytes) {
 
 // the scratch a launch works in: the store's own arrays, or -- for an overlap launch planned by the plan kernels --
 // slot (sequence number & 3)
+// The plan kernel tags its look-back words with a 22-bit launch counter instead of clearing them; shortly before the
+// counter wraps, clear every scratch area once and start over.
+int renew_plan_tags(dds_store *s) {
+    if (s->scr.plan_tag < 0x3FFFF0u) return DDS_OK;
+    CU(device_sync(s));
+    s->run_len = 0;
+    if (s->scr.tile_sums) CU(cudaMemset(s->scr.tile_sums, 0, (size_t)(s->scr.cap_req / 1024 + 2) * 8));
+    for (auto &sl : s->slots)
+        if (sl.tile_sums) CU(cudaMemset(sl.tile_sums, 0, (size_t)(sl.cap_req / 1024 + 2) * 8));
+    s->scr.plan_tag = 0;
+    return DDS_OK;
+}
+
 ddsk_scratch_t scratch_view(dds_store *s, bool slot) {
     ddsk_scratch_t v = s->scr;
     if (slot) {
@@ -261,7 +383,7 @@ int ensure_offs(dds_store *s, int64_t n) {
     if (n <= s->offs_cap) return DDS_OK;
     int64_t cap = std::max<int64_t>(4096, s->offs_cap);
     while (cap < n) cap *= 2;
-    CU(cudaDeviceSynchronize());
+    CU(device_sync(s));
     if (s->d_offs) cudaFree(s->d_offs);
     s->d_offs = nullptr;
     s->offs_cap = 0;
@@ -551,6 +673,11 @@ int register_var(dds_store *s, const char *name, const void *buffer, int64_t nro
     }
     v.kv.row_bytes = (int64_t)disp * (int64_t)itemsize;
     v.kv.nranks = s->size;
+    if (s->db_enabled && s->d_vars && s->next_var_id < dds_store::kMaxDbVars) { // window into the doorbell kernel's table
+        if (cudaMemcpy(&s->d_vars[s->next_var_id], &v.kv, sizeof(ddsk_var_t), cudaMemcpyHostToDevice) == cudaSuccess)
+            v.id = s->next_var_id++;
+        (void)cudaGetLastError();
+    }
     s->vars.emplace(v.name, std::move(v));
     return brc;
 }
@@ -664,16 +791,26 @@ dds_store_t *dds_create(dds_comm_t *comm, int device, int method) {
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc((void **)&s->scr.status, 16) == cudaSuccess && // [0] sticky status, [1] packed total
-              cudaMalloc((void **)&s->scr.counters, 64) == cudaSuccess && // 2 ticket words + 8 overlap-protocol words
-              cudaMemset(s->scr.counters, 0, 64) == cudaSuccess &&
+              cudaMalloc((void **)&s->scr.counters, 256) == cudaSuccess && // 2 ticket words (+pad), 24 protocol words, 4 plan words
+              cudaMemset(s->scr.counters, 0, 256) == cudaSuccess &&
               cudaMemset(s->scr.status, 0xFF, 8) == cudaSuccess &&
               cudaHostAlloc((void **)&s->h_status, 32, cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void **)&s->scr.host_mirror, s->h_status, 0) == cudaSuccess &&
               cudaHostAlloc((void **)&s->h_small, (size_t)(kSmallIdx * 16 + kSmallOut), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void **)&s->d_small, s->h_small, 0) == cudaSuccess;
+    if (const char *e = getenv("DDS_DOORBELL")) s->db_enabled = atoi(e) != 0;
+    if (const char *e = getenv("DDS_DOORBELL_IDLE_US")) s->db_idle_ns = (unsigned long long)std::max(1, atoi(e)) * 1000ull;
+    if (ok && s->db_enabled) {
+        ok = cudaHostAlloc((void **)&s->h_mb, sizeof(ddsk_mailbox_t), cudaHostAllocMapped) == cudaSuccess &&
+             cudaHostGetDevicePointer((void **)&s->d_mb, s->h_mb, 0) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&s->db_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaMalloc((void **)&s->d_vars, sizeof(ddsk_var_t) * dds_store::kMaxDbVars) == cudaSuccess;
+        if (ok) memset(s->h_mb, 0, sizeof(ddsk_mailbox_t));
+    }
     if (ok) {
         s->scr.total = (int64_t *)(s->scr.status + 1);
         s->scr.ovl = s->scr.counters + 8;
+        s->scr.plan_word = (unsigned long long *)(s->scr.counters + 32);
         memset(s->h_status, 0, 32);
     }
     if (!ok) {
@@ -742,6 +879,78 @@ int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64
                        cuda_stream ? (cudaStream_t)cuda_stream : (s ? s->stream : nullptr), false);
 }
 
+int dds_ingest(dds_store_t *s, const char *name, const void *host_rows, int64_t nrows, int64_t offset, int itemsize) {
+    // update<T> (ddstore.hpp:181-195) for a chunk of PAGEABLE host rows, pipelined: parallel CPU copy into pinned staging
+    // buffers + async H2D. Returns once the source has been consumed (the caller may reuse it); the last copies complete
+    // at the next fence, dds_ingest_wait, or free.
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE); // ddstore.hpp:189-190
+    if (nrows < 0 || offset < 0 || offset + nrows > v->nrows)
+        return fail(DDS_ERR_ARG, "update outside the local shard (unchecked memcpy in the reference)");
+    const size_t row = (size_t)v->disp * (size_t)v->itemsize;
+    size_t total = (size_t)nrows * row;
+    if (total == 0) return DDS_OK;
+    if (!host_rows) return fail(DDS_ERR_ARG, "null buffer");
+    CU(cudaSetDevice(s->device));
+    if (!s->ingest) {
+        IngestPool *p = new IngestPool;
+        bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; k++)
+            ok = cudaHostAlloc((void **)&p->pin[k], IngestPool::kStage, cudaHostAllocDefault) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            cudaError_t e = cudaGetLastError();
+            for (int k = 0; k < 2; k++) {
+                if (p->pin[k]) cudaFreeHost(p->pin[k]);
+                if (p->ev[k]) cudaEventDestroy(p->ev[k]);
+            }
+            if (p->stream) cudaStreamDestroy(p->stream);
+            delete p;
+            return cuda_fail(e, "dds_ingest: staging setup");
+        }
+        int nt = 6;
+        if (const char *e = getenv("DDS_INGEST_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+        cpu_set_t cs;
+        if (sched_getaffinity(0, sizeof(cs), &cs) == 0) nt = std::max(1, std::min(nt, CPU_COUNT(&cs)));
+        p->start(nt);
+        s->ingest = p;
+    }
+    IngestPool *p = s->ingest;
+    const char *src = (const char *)host_rows;
+    char *dst = (char *)v->base + (size_t)offset * row;
+    while (total) {
+        const size_t n = std::min(total, IngestPool::kStage);
+        const int k = p->next;
+        if (p->ev_pending[k]) { // the H2D copy that last used this staging buffer
+            CU(cudaEventSynchronize(p->ev[k]));
+            p->ev_pending[k] = false;
+        }
+        p->copy(p->pin[k], src, n);
+        CU(cudaMemcpyAsync(dst, p->pin[k], n, cudaMemcpyHostToDevice, p->stream));
+        CU(cudaEventRecord(p->ev[k], p->stream));
+        p->ev_pending[k] = true;
+        p->next ^= 1;
+        src += n;
+        dst += n;
+        total -= n;
+    }
+    s->update_streams.insert(p->stream); // the next fence / free waits for the tail
+    return DDS_OK;
+}
+
+int dds_ingest_wait(dds_store_t *s) {
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    if (!s->ingest) return DDS_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->ingest->stream));
+    s->ingest->ev_pending[0] = s->ingest->ev_pending[1] = false;
+    return DDS_OK;
+}
+
 // every copy queued by dds_update_async on a caller's stream has landed (the fences promise the shard is complete)
 static int drain_update_streams(dds_store_t *s) {
     for (cudaStream_t st : s->update_streams) {
@@ -776,8 +985,74 @@ static int overlap_flags(dds_store_t *s, bool ovl, bool chain) {
 
 // One request through the 1-CTA kernel: the legacy one-get()-per-sample call. One launch, no stream synchronize: the
 // kernel's last store is a ticket in mapped pinned memory the host spins on.
+static int doorbell_launch(dds_store_t *s, unsigned long long served) {
+    s->db_gen++;
+    if (ddsk_doorbell_launch(s->d_vars, s->d_mb, served, s->db_gen, s->db_idle_ns, s->db_stream))
+        return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    s->db_alive = true;
+    return DDS_OK;
+}
+
+// The launch-free form of small_get: post the request in the mailbox of the resident doorbell CTA (starting one if none
+// is alive) and spin on its one-word answer.
+static int doorbell_get(dds_store_t *s, Var *v, int64_t start, int64_t count, void *dst, int64_t cap, bool dst_dev,
+                        int64_t *total_bytes, int64_t *bad_index) {
+    volatile ddsk_mailbox_t *mb = s->h_mb;
+    if (s->db_alive && mb->exit_gen == s->db_gen) s->db_alive = false; // it left on its own (idle)
+    if (!s->db_alive) {
+        if (int rc = doorbell_launch(s, s->db_seq)) return rc;
+    }
+    mb->start = start;
+    mb->count = count;
+    mb->dst = (uint64_t)(dst_dev ? dst : (void *)(s->d_small + kSmallIdx * 16));
+    mb->dst_cap = cap;
+    mb->var_stop = (uint64_t)(uint32_t)v->id;
+    std::atomic_thread_fence(std::memory_order_release);
+    const unsigned long long seq = ++s->db_seq;
+    mb->seq_tail = seq;
+    std::atomic_thread_fence(std::memory_order_release);
+    mb->seq_head = seq;
+    unsigned long long r = 0;
+    for (unsigned spins = 0;; spins++) {
+        r = mb->resp;
+        if ((r >> 8) == seq) break;
+        if (mb->exit_gen == s->db_gen) { // the kernel left; unless it answered first, a fresh one takes the request
+            r = mb->resp;
+            if ((r >> 8) == seq) break;
+            cudaError_t e = cudaStreamSynchronize(s->db_stream);
+            if (e != cudaSuccess) {
+                s->db_alive = false;
+                return cuda_fail(e, "doorbell kernel");
+            }
+            if (int rc = doorbell_launch(s, seq - 1)) return rc;
+        }
+        if ((spins & 0xFFFF) == 0xFFFF) {
+            cudaError_t q = cudaStreamQuery(s->db_stream);
+            if (q != cudaErrorNotReady && q != cudaSuccess) {
+                s->db_alive = false;
+                return cuda_fail(q, "doorbell kernel");
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const int code = (int)(r & 0xFFu);
+    const int64_t n = code ? 0 : (count > 0 ? count * v->kv.row_bytes : 0);
+    if (!dst_dev && n > 0) memcpy(dst, s->h_small + kSmallIdx * 16, (size_t)n);
+    if (total_bytes) *total_bytes = n;
+    if (!code) {
+        if (bad_index) *bad_index = -1;
+        return DDS_OK;
+    }
+    return decode_status_word(code == DDSK_CODE_CAPACITY ? (((unsigned long long)1 << 8) | DDSK_CODE_CAPACITY)
+                                                          : (unsigned long long)code, bad_index);
+}
+
 static int small_get(dds_store_t *s, Var *v, int64_t start, int64_t count, void *dst, int64_t cap, bool dst_dev,
                      int64_t *total_bytes, int64_t *bad_index) {
+    if (s->db_enabled && v->id >= 0) return doorbell_get(s, v, start, count, dst, cap, dst_dev, total_bytes, bad_index);
     cudaStream_t st = s->stream;
     volatile unsigned long long *flag = s->h_status;
     const unsigned long long ticket = ++s->small_ticket;
@@ -903,6 +1178,7 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
     const bool ovl = no_sync && (flags & DDS_OVERLAP);
     const bool uses_scratch = !fixed && ddsk_var_uses_scratch(nreq, cap);
     if (uses_scratch) {
+        if (int rc = renew_plan_tags(s)) return rc;
         if (int rc = ovl ? ensure_slots(s, nreq, cap) : ensure_scratch(s, nreq, cap)) return rc;
     }
 
@@ -929,6 +1205,7 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             ix.counts = d_counts;
         }
         krc = ddsk_gather_var(&v->kv, &ix, nreq, d_dst, cap, d_offsets, &scr, kflags, st);
+        s->scr.plan_tag = scr.plan_tag;
         s->pending_total_ptr = uses_scratch ? &scr.req_dst[nreq] : s->scr.total;
     }
     if (krc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
@@ -991,7 +1268,7 @@ int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_st
     if (nsamples < 0 || (nsamples > 0 && (!row_start || !row_count))) return fail(DDS_ERR_ARG, "bad sample index");
     CU(cudaSetDevice(s->device));
     if (s->pending) dds_batch_wait(s, nullptr, nullptr);
-    CU(cudaDeviceSynchronize()); // no queued launch may still be reading the old table
+    CU(device_sync(s)); // no queued launch may still be reading the old table
     if (v->d_tab) cudaFree(v->d_tab);
     v->d_tab = nullptr;
     v->h_tab_count.clear();
@@ -1071,6 +1348,7 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
     const bool ovl = no_sync && (flags & DDS_OVERLAP);
     const bool uses_scratch = ddsk_var_uses_scratch(nreq * nvars, cap_total);
     if (uses_scratch) {
+        if (int rc = renew_plan_tags(s)) return rc;
         if (int rc = ovl ? ensure_slots(s, nreq * nvars, cap_total) : ensure_scratch(s, nreq * nvars, cap_total)) return rc;
     }
     // a synchronous caller wants the per-variable totals: they are the last entries of the per-variable offsets, which
@@ -1092,7 +1370,9 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
     }
     const int kflags = (no_sync ? 0 : DDSK_F_MIRROR) | overlap_flags(s, ovl, chain);
     ddsk_scratch_t scr = scratch_view(s, uses_scratch && ovl);
-    if (ddsk_gather_multi(&m, d_ids, nreq, &scr, kflags, st)) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    const int mrc = ddsk_gather_multi(&m, d_ids, nreq, &scr, kflags, st);
+    s->scr.plan_tag = scr.plan_tag;
+    if (mrc) return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
     s->pending_fixed_total = -1;
     s->pending_nreq = nreq * nvars;
     s->pending_total_ptr = uses_scratch ? &scr.req_dst[nreq * nvars] : s->scr.total;
@@ -1201,7 +1481,7 @@ int dds_free(dds_store_t *s) {
     CU(cudaSetDevice(s->device));
     if (s->pending) dds_batch_wait(s, nullptr, nullptr);
     s->update_streams.clear();
-    CU(cudaDeviceSynchronize());
+    CU(device_sync(s));
     int rc = dds_comm_barrier(s->comm); // nobody is reading any more
     local_release(s);
     int rc2 = dds_comm_barrier(s->comm); // every mapping is closed before the memory goes away
@@ -1226,7 +1506,7 @@ void dds_destroy(dds_store_t *s) {
     for (auto &x : s->vars) unprotected |= x.second.unprotected_peers;
     if (unprotected && s->size > 1) (void)dds_free(s);
     if (cudaSetDevice(s->device) == cudaSuccess) {
-        cudaDeviceSynchronize();
+        device_sync(s);
         local_release(s);
         for (auto &x : s->vars) free_shard(x.second);
         for (void *z : s->zombies) cudaFree(z);
@@ -1249,6 +1529,20 @@ void dds_destroy(dds_store_t *s) {
         if (s->d_offs) cudaFree(s->d_offs);
         if (s->h_status) cudaFreeHost(s->h_status);
         if (s->h_small) cudaFreeHost(s->h_small);
+        if (s->ingest) {
+            s->ingest->stop();
+            cudaStreamSynchronize(s->ingest->stream);
+            for (int k = 0; k < 2; k++) {
+                cudaFreeHost(s->ingest->pin[k]);
+                cudaEventDestroy(s->ingest->ev[k]);
+            }
+            cudaStreamDestroy(s->ingest->stream);
+            delete s->ingest;
+            s->ingest = nullptr;
+        }
+        if (s->h_mb) cudaFreeHost(s->h_mb);
+        if (s->d_vars) cudaFree(s->d_vars);
+        if (s->db_stream) cudaStreamDestroy(s->db_stream);
         if (s->d_multi_vars) cudaFree(s->d_multi_vars);
         if (s->stream) cudaStreamDestroy(s->stream);
     }

@@ -40,12 +40,16 @@ class DistDataset(Dataset):
         self.label = label
         self.comm = as_dds_comm(comm)
         self.rank, self.comm_size = self.comm.Get_rank(), self.comm.Get_size()
-        if ddstore_width is not None and ddstore_width != self.comm_size:
-            # the reference splits the communicator into replica groups of this width (distdataset.py:25-30);
-            # here a store spans one NVSwitch box, so pass the per-box communicator instead
-            raise NotImplementedError("pass the per-box communicator instead of ddstore_width")
+        # replica groups exactly as the reference builds them (distdataset.py:25-30): consecutive ranks in groups of
+        # `ddstore_width`, every group holding the WHOLE dataset sharded over its members (one group per NVSwitch box)
+        self.ddstore_width = ddstore_width if ddstore_width is not None else self.comm_size
+        if self.ddstore_width != self.comm_size:
+            self.ddstore_comm = self.comm.Split(self.rank // self.ddstore_width, self.rank)
+        else:
+            self.ddstore_comm = self.comm
+        self.ddstore_comm_rank, self.ddstore_comm_size = self.ddstore_comm.Get_rank(), self.ddstore_comm.Get_size()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.ddstore = PyDDStore(self.comm, device=self.device.index)
+        self.ddstore = PyDDStore(self.ddstore_comm, device=self.device.index)
 
         if local_only:
             mine = list(range(len(data)))
@@ -53,7 +57,7 @@ class DistDataset(Dataset):
             self.total_ns = sum(counts)
         else:
             self.total_ns = len(data)
-            mine = list(nsplit(range(len(data)), self.comm_size))[self.rank]
+            mine = list(nsplit(range(len(data)), self.ddstore_comm_size))[self.ddstore_comm_rank]
         vals, labels = [], []
         for i in mine:
             d, lab = data[i]
@@ -64,11 +68,12 @@ class DistDataset(Dataset):
         arr = np.stack(vals) if vals else np.zeros((0, 1), np.float32)
         self.sample_size = arr.shape[1]
         self.dtype = torch.from_numpy(arr[:0]).dtype
+        self._np_dtype = arr.dtype
         self.ddstore.add(f"{self.label}data", np.ascontiguousarray(arr))
         self.ddstore.add(f"{self.label}labels", np.ascontiguousarray(np.array(labels, dtype=np.int32).reshape(-1, 1)))
 
     def _allgather_int(self, v):
-        parts = self.comm.allgather_bytes(int(v).to_bytes(8, "little"))
+        parts = self.ddstore_comm.allgather_bytes(int(v).to_bytes(8, "little"))
         return [int.from_bytes(p, "little") for p in parts]
 
     def len(self):
@@ -77,13 +82,13 @@ class DistDataset(Dataset):
     def __len__(self):
         return self.total_ns
 
-    # ---- the reference's per-sample contract (distdataset.py:79-92)
+    # ---- the reference's per-sample contract (distdataset.py:79-92): host buffers in, a CPU tensor + an int out
     def get(self, idx):
-        val = torch.empty(self.sample_size, dtype=self.dtype, device=self.device)
-        lab = torch.empty(1, dtype=torch.int32, device=self.device)
-        self.ddstore.get(f"{self.label}data", val.view(1, -1), int(idx))
-        self.ddstore.get(f"{self.label}labels", lab.view(1, 1), int(idx))
-        return val.view(self.sample_shape), int(lab.item())
+        val = np.empty((1, self.sample_size), dtype=self._np_dtype)
+        lab = np.empty((1, 1), dtype=np.int32)
+        self.ddstore.get(f"{self.label}data", val, int(idx))
+        self.ddstore.get(f"{self.label}labels", lab, int(idx))
+        return torch.from_numpy(val).view(self.sample_shape), int(lab[0, 0])
 
     def __getitem__(self, idx):
         return self.get(idx)
@@ -94,8 +99,11 @@ class DistDataset(Dataset):
         idx = np.asarray(indices, dtype=np.int64)
         vals = torch.empty((B, self.sample_size), dtype=self.dtype, device=self.device)
         labs = torch.empty((B, 1), dtype=torch.int32, device=self.device)
-        self.ddstore.get_batch(f"{self.label}data", idx, out=vals, count=1)
-        self.ddstore.get_batch(f"{self.label}labels", idx, out=labs, count=1)
+        # on torch's CURRENT stream: the output tensors come from its caching allocator, whose blocks may still be in use
+        # by work queued there, and the index copy + the gather are then ordered with everything the caller queued before
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.ddstore.get_batch(f"{self.label}data", idx, out=vals, count=1, stream=st)
+        self.ddstore.get_batch(f"{self.label}labels", idx, out=labs, count=1, stream=st)
         return vals.view((B,) + self.sample_shape), labs.view(B)
 
     @staticmethod
@@ -163,8 +171,10 @@ class RaggedDataset(Dataset):
     def __getitems__(self, indices):
         """-> {name: (packed rows tensor [sum(count), ...width], int64 row offsets per sample [B+1])}.
         One launch chain per variable; the sample-id -> (start, count) lookup happens on the device."""
-        ids = np.asarray(indices, dtype=np.int64)
-        d_ids = torch.from_numpy(ids).to(self.device, non_blocking=True)
+        ids = np.ascontiguousarray(indices, dtype=np.int64)
+        # host ids go to the store as they are: it copies them on the stream the gather runs on (torch's current stream:
+        # the outputs below come from that stream's allocator), so the kernel can never read them before they landed
+        st = torch.cuda.current_stream(self.device).cuda_stream
         out, bufs, offs, rows = {}, [], [], []
         for name in self.names:
             r = int(self.counts[name][ids].sum())  # host-side size of the packed result (sizes only, no data)
@@ -173,10 +183,10 @@ class RaggedDataset(Dataset):
             offs.append(torch.empty(len(ids) + 1, dtype=torch.int64, device=self.device))
         if len(self.names) <= 4:
             # every variable of the batch in ONE launch (dds_get_samples_multi)
-            self.ddstore.get_samples_multi(self.names, d_ids, bufs, offsets=offs)
+            self.ddstore.get_samples_multi(self.names, ids, bufs, offsets=offs, stream=st)
         else:
             for name, buf, off in zip(self.names, bufs, offs):
-                self.ddstore.get_samples(name, d_ids, out=buf, offsets=off)
+                self.ddstore.get_samples(name, ids, out=buf, offsets=off, stream=st)
         for name, buf, off, r in zip(self.names, bufs, offs, rows):
             out[name] = (buf[:r], off // self.row_bytes[name])
         return out
@@ -274,26 +284,17 @@ class PrefetchLoader:
 
 
 def ingest_chunks(store, name, chunks, first_row=0):
-    """Streaming ingest: fill a pre-`init`'d shard from an iterator of host arrays
-    (the reference's init + update-in-chunks pattern, include/ddstore.hpp:110-195) through a pinned double buffer,
-    so producing / reading chunk k+1 on the host overlaps the H2D copy of chunk k. Returns rows written."""
-    stream = torch.cuda.Stream()
-    pinned, events, k, row = [None, None], [None, None], 0, int(first_row)
+    """Streaming ingest: fill a pre-`init`'d shard from an iterator of host arrays (the
+    reference's init + update-in-chunks pattern, include/ddstore.hpp:110-195). Every chunk goes through the library's
+    pipelined path (`dds_ingest`: worker threads stage slices of the chunk into pinned buffers while the copy engine
+    moves the previous buffer), so producing / reading chunk k+1 on the host overlaps the H2D copy of chunk k's tail.
+    Returns rows written."""
+    row = int(first_row)
     for chunk in chunks:
         arr = np.ascontiguousarray(chunk)
-        slot = k & 1
-        if events[slot] is not None:
-            events[slot].synchronize()  # the copy that used this pinned buffer two chunks ago is done
-        if pinned[slot] is None or pinned[slot].numel() < arr.nbytes:
-            pinned[slot] = torch.empty(max(arr.nbytes, 1), dtype=torch.uint8).pin_memory()
-        stage = pinned[slot][:arr.nbytes].numpy().view(arr.dtype).reshape(arr.shape)
-        stage[...] = arr
-        store.update(name, stage, row, stream=stream.cuda_stream, wait=False)  # bounds-checked H2D, no sync
-        events[slot] = torch.cuda.Event()
-        events[slot].record(stream)
+        store.ingest(name, arr, row)  # bounds-checked; returns when `arr` has been consumed
         row += arr.shape[0]
-        k += 1
-    stream.synchronize()
+    store.ingest_wait()
     return row - int(first_row)
 
 

@@ -107,6 +107,17 @@ class PyDDStore:
                                           b.on_device, self._stream_arg(stream))
         _capi.raise_for(rc)
 
+    def ingest(self, name, arr, offset):
+        """update() for a chunk of pageable host rows, pipelined inside the library (parallel staging copy + async H2D).
+        Returns when `arr` has been consumed; call ingest_wait() (or an epoch fence) before reading the rows back."""
+        b = _Buf(arr)
+        if b.on_device:
+            raise ValueError("ingest takes host arrays (use update for device arrays)")
+        _capi.raise_for(self._L.dds_ingest(self._h, name.encode(), b.ptr, b.shape[0], int(offset), b.itemsize))
+
+    def ingest_wait(self):
+        _capi.raise_for(self._L.dds_ingest_wait(self._h))
+
     # ---------------------------------------------------------------- the batched hot path
     def get_batch(self, name, starts, counts=None, out=None, count=None, offsets=None, stream=None, wait=True,
                   overlap=False):
@@ -122,6 +133,11 @@ class PyDDStore:
         `wait()` later for the status. Several such batches may be queued on one stream.
         overlap=True (with wait=False): this batch is independent of the one queued just before it (different `out`
         and `offsets`, indices not written by it) and may overlap with its tail -- double-buffered prefetch.
+        stream: the cudaStream_t handle everything of this call is enqueued on (index copy, kernels, result copy).
+        stream=None means the STORE'S OWN stream, which is not ordered with anything the caller has queued elsewhere:
+        device tensors passed in (indices, out, offsets) must then be complete / free to overwrite before the call --
+        e.g. produced by a synchronous copy. When they were produced or are consumed on torch's current stream, pass
+        stream=torch.cuda.current_stream().cuda_stream.
         Raises the reference's ValueError for the first invalid request (requests before it are delivered).
         """
         itemsize = self._itemsize.get(name)

@@ -115,6 +115,12 @@ int dds_update(dds_store_t *s, const char *name, const void *buffer, int64_t nro
  * pre-init'd shard from pinned chunks (the copy of chunk k overlaps the host producing chunk k+1). */
 int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64_t nrows, int64_t offset, int itemsize,
                      int buffer_on_device, void *cuda_stream);
+/* dds_update for a chunk of PAGEABLE host rows, pipelined inside the library: a few worker threads copy slices of the
+ * chunk into pinned staging buffers while the copy engine moves the previous buffer into the shard (streaming ingest of
+ * a pre-init'd shard, the reference's init + update-in-chunks pattern). Returns once the source has been consumed; the
+ * tail of the copies completes at the next epoch fence, dds_ingest_wait or dds_free. DDS_INGEST_THREADS (default 6). */
+int dds_ingest(dds_store_t *s, const char *name, const void *host_rows, int64_t nrows, int64_t offset, int itemsize);
+int dds_ingest_wait(dds_store_t *s);
 /* template<T> void get(string name, long start, long count, T* buffer), ddstore.hpp:197-248. Fetches
  * count rows starting at GLOBAL row `start` (must lie within one owner) into `buffer` (host, or device).
  * Results up to 64 KiB (host) / 1 MiB (device) take a 1-CTA kernel whose completion the host spins on in mapped

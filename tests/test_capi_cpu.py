@@ -130,6 +130,31 @@ def test_shm_comm_threads_allgather_barrier_lenlist():
         assert rc == 0 and ll == [1000, 3500, 3500, 10000]  # include/ddstore.hpp:84-89
 
 
+def test_comm_split_builds_the_reference_replica_groups():
+    """comm.Split(rank // width, rank) as in examples/vae/distdataset.py:28: consecutive ranks in groups of `width`,
+    each group with its own rank numbering, allgather and lenlist"""
+    P, width = 6, 2
+
+    def body(c, r):
+        sub = c.Split(r // width, r)
+        try:
+            assert sub.Get_size() == width and sub.Get_rank() == r % width
+            parts = sub.allgather_bytes(bytes([r]))
+            sub.Barrier()
+            return [p[0] for p in parts], _exchange(sub, 10 * (r + 1), 2)
+        finally:
+            sub.close()
+
+    res = _thread_world(P, body)
+    for r, (members, (rc, ll)) in enumerate(res):
+        g = r // width
+        assert members == [g * width, g * width + 1] and rc == 0
+        assert ll == [10 * (g * width + 1), 10 * (g * width + 1) + 10 * (g * width + 2)]
+    # an uneven split (key reverses the order inside the colour)
+    res = _thread_world(5, lambda c, r: (lambda s: (s.Get_rank(), s.Get_size(), s.close())[:2])(c.Split(r % 2, -r)))
+    assert res == [(2, 3), (1, 2), (1, 3), (0, 2), (0, 3)]
+
+
 def test_lenlist_disp_mismatch_raises_on_the_differing_ranks():
     # include/ddstore.hpp:78-82: ranks whose disp != max(disp) throw "Invalid disp"
     def body(c, r):

@@ -43,8 +43,8 @@ def test_distdataset_per_sample_and_batched_loader():
         ds = DistDataset(data, "train", comm=comm, device=0)
         assert len(ds) == N
         for idx in (0, 499, 500, 999, int(rng.integers(N))):
-            val, lab = ds[idx]  # the reference's per-sample path (distdataset.py:79-92)
-            assert val.shape == (1, 8, 8) and val.cpu().numpy().tobytes() == images[idx].tobytes() and lab == labels[idx]
+            val, lab = ds[idx]  # the reference's per-sample path (distdataset.py:79-92): a CPU tensor and an int
+            assert not val.is_cuda and val.shape == (1, 8, 8) and val.numpy().tobytes() == images[idx].tobytes() and lab == labels[idx]
         seen = []
         loader = make_loader(ds, batch_size=64, rank=r, world_size=P, shuffle=True, seed=7)
         for epoch in range(2):
@@ -65,6 +65,37 @@ def test_distdataset_per_sample_and_batched_loader():
 
     parts = _world(P, body)
     assert parts[0] | parts[1] == set(range(N))
+
+
+def test_ddstore_width_replica_groups():
+    """ddstore_width < comm size: the communicator is split into replica groups of that width exactly as the reference
+    does (examples/vae/distdataset.py:25-30); every group holds the WHOLE dataset sharded over its own members, the
+    groups' stores are disjoint, and any rank can fetch any sample from its own group"""
+    from ddstore_b200.dataset import DistDataset
+    rng = np.random.default_rng(11)
+    N, P, width = 600, 4, 2
+    images = rng.integers(0, 2**32, size=(N, 6), dtype=np.uint32).view(np.float32)
+    labels = rng.integers(0, 10, size=N)
+    data = [(images[i], int(labels[i])) for i in range(N)]
+
+    def body(comm, r):
+        ds = DistDataset(data, "w", comm=comm, ddstore_width=width, device=0)
+        assert ds.ddstore_comm_size == width and ds.ddstore_comm_rank == r % width and ds.ddstore.size == width
+        info = ds.ddstore.query("wdata")
+        assert info["nranks"] == width and info["lenlist"] == [N // 2, N] and len(ds) == N
+        ids = rng.integers(0, N, size=97)
+        vals, labs = ds.__getitems__(ids.tolist())
+        assert vals.cpu().numpy().tobytes() == images[ids].tobytes() and np.array_equal(labs.cpu().numpy(), labels[ids])
+        v, lab = ds[int(ids[0])]
+        assert v.numpy().tobytes() == images[ids[0]].tobytes() and lab == labels[ids[0]]
+        base = info["local_base"]
+        ds.free()
+        ds.ddstore.close()
+        ds.ddstore_comm.close()
+        return base
+
+    bases = _world(P, body)
+    assert len(set(bases)) == P  # four distinct shards: two per replica group
 
 
 def test_ragged_dataset_config4_shape():
