@@ -615,7 +615,8 @@ def run_configs(ctx, args, names, ref):
     if "cfg5" in names:
         sweep += [(R_, f"cfg5_R{R_}", max(1, (256 << 20) // R_)) for R_ in CFG5_SIZES]
     if "cfg1" in names:
-        sweep += [(512, "cfg1_rows512_B4096", 4096), (512, "cfg1_rows512_B262144", 262144)]
+        # (the last one = 16 loader batches of 4096 served by ONE launch: PrefetchLoader(group=16))
+        sweep += [(512, "cfg1_rows512_B4096", 4096), (512, "cfg1_rows512_B4096_group16", 65536), (512, "cfg1_rows512_B262144", 262144)]
     for R_, key, B in sweep:
         shard = max(int((1 << 30) * sc), 64 * R_)
         rows = shard // R_

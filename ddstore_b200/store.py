@@ -66,6 +66,7 @@ class PyDDStore:
             raise RuntimeError(_capi.last_error())
         self.rank, self.size = self._L.dds_rank(self._h), self._L.dds_size(self._h)
         self._itemsize = {}  # per-variable itemsize, cached for the hot path
+        self._cname = {}     # name -> bytes, cached for the per-sample get() loop
         self.last_bad_index = -1
 
     # ---------------------------------------------------------------- reference surface
@@ -78,9 +79,19 @@ class PyDDStore:
 
     def get(self, name, arr, start=0):
         # src/pyddstore.pyx:84-101: count = arr.shape[0]; fills arr in place
-        b = _Buf(arr, writable=True)
-        count = b.shape[0]
-        _capi.raise_for(self._L.dds_get(self._h, name.encode(), int(start), count, b.itemsize, b.ptr, b.on_device))
+        cn = self._cname.get(name)
+        if cn is None:
+            cn = self._cname[name] = name.encode()
+        if type(arr) is np.ndarray:  # the legacy per-sample loop: keep the Python side of the call short
+            assert arr.flags.c_contiguous
+            if arr.dtype not in _NP_OK:
+                raise NotImplementedError
+            rc = self._L.dds_get(self._h, cn, int(start), arr.shape[0], arr.dtype.itemsize, arr.ctypes.data, 0)
+        else:
+            b = _Buf(arr, writable=True)
+            rc = self._L.dds_get(self._h, cn, int(start), b.shape[0], b.itemsize, b.ptr, b.on_device)
+        if rc:
+            _capi.raise_for(rc)
 
     def epoch_begin(self):
         _capi.raise_for(self._L.dds_epoch_begin(self._h))  # src/pyddstore.pyx:103-104
