@@ -66,6 +66,9 @@ SIGNATURES = {
     "dds_epoch_end": (C.c_int, [C.c_void_p]),
     "dds_free": (C.c_int, [C.c_void_p]),
     "dds_synth_fill": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "dds_push_setup": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "dds_get_batch_push": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_void_p),
+                                    C.c_void_p]),
     "dds_ingest": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
     "dds_ingest_wait": (C.c_int, [C.c_void_p]),
     "dds_synth_verify": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,

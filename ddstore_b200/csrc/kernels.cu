@@ -149,6 +149,17 @@ __device__ __forceinline__ int dev_locate(const ddsk_var_t &v, int64_t start, in
     return 0;
 }
 
+// same, also returning the owner rank (the collective push fetch lets only the owner act on a request)
+__device__ __forceinline__ int dev_locate_owner(const ddsk_var_t &v, int64_t start, int64_t count, uint64_t *src, int *owner) {
+    int t = dev_sortedsearch(v, start);
+    *owner = t;
+    int64_t off = t > 0 ? v.lenlist[t - 1] : 0;
+    if (start < off) return DDSK_CODE_START;
+    if (count < 0 || start + count > v.lenlist[t]) return DDSK_CODE_COUNT;
+    *src = (uint64_t)v.bases[t] + (uint64_t)(start - off) * (uint64_t)v.row_bytes;
+    return 0;
+}
+
 __device__ __forceinline__ void report(unsigned long long *status, int64_t req, int code) {
     atomicMin(status, ((unsigned long long)req << 8) | (unsigned long long)code);
 }
@@ -183,6 +194,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// system scope: words other GPUs poll / write over NVLink (collective push fetch)
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int64_t ld_relaxed_sys_s64(const int64_t *p) {
+    int64_t v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -344,6 +369,12 @@ struct GatherArgs {
     unsigned int *tickets;        // the segment ticket word of this launch (counters[0], or ovl[8 + slot]); NULL: static striding
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
     unsigned long long *dbg;         // DDS_DEBUG_TIMING: per CTA [entry, plan done, first data, last warp done] (globaltimer ns)
+    // ---- collective owner-push fetch (FIXED only; see the protocol at dds_gather_kernel's push section)
+    const ddsk_push_t *push; // device copy of the windows' table; NULL: ordinary (pull) batch
+    const int64_t *push_src_idx; // this rank's index list for the step (copied into its window by CTA 0)
+    int64_t push_nreq;           // ... and its length
+    unsigned long long push_step;
+    unsigned int *push_counters; // [0] warps finished
 };
 
 // the walk's granularity for segment tables: segment sizes of variable-count launches are multiples of this
@@ -386,6 +417,12 @@ struct ChunkWalker {
     int64_t cur_seg = 0;
     unsigned int pend = 0; // lane 0: ticket claimed ahead of need (the atomic's latency hides behind the current segment)
     int64_t r = 0, win_base = -64;
+    int64_t nreq = 0; // requests of the walk (a.nreq; the sum over all requesters in a collective push fetch)
+    // collective push fetch: the walk runs over the concatenation of every requester's list
+    int push_n = 0, push_me = 0, push_par = 0;
+    const int64_t *push_rbase = nullptr;  // shared memory: [push_n + 1] first virtual request of requester p
+    const uint64_t *push_win = nullptr;   // shared memory: [push_n] window of requester p
+    int64_t push_idx_off = 0;
     PlanView<PCAP> pv;
     // per-lane window of 32 request descriptors
     uint64_t w_src = 0;
@@ -397,8 +434,26 @@ struct ChunkWalker {
         w_src = 0;
         w_dst = 0;
         w_n = 0;
-        if (idx < a.nreq) {
-            if (FIXED) {
+        if (idx < nreq) {
+            if (FIXED && push_n > 0) {
+                // which requester's list does virtual request idx belong to, and which entry of it?
+                int p = 0;
+                for (int k = 1; k < push_n; k++)
+                    if (idx >= push_rbase[k]) p = k;
+                const int64_t i = idx - push_rbase[p];
+                const int64_t start = ld_relaxed_sys_s64((const int64_t *)(push_win[p] + push_idx_off) + i);
+                uint64_t s = 0;
+                int owner = 0;
+                const int code = dev_locate_owner(a.var, start, a.count, &s, &owner);
+                // only the owner acts on a request: it pushes the rows, or tells the requester what is wrong with it
+                if (code && owner == push_me) {
+                    unsigned long long *st = (unsigned long long *)push_win[p] + 3;
+                    asm volatile("red.relaxed.sys.global.min.u64 [%0], %1;" ::"l"(st), "l"(((unsigned long long)i << 8) | (unsigned long long)code) : "memory");
+                }
+                w_src = (code || owner != push_me) ? 0 : s;
+                w_dst = idx * nb;
+                w_n = nb;
+            } else if (FIXED) {
                 uint64_t s = 0;
                 int code = dev_locate(a.var, a.starts[idx], a.count, &s);
                 if (code) report(a.status, idx, code); // the reference's two checks; every request with bytes to
@@ -423,7 +478,7 @@ struct ChunkWalker {
             // the request whose bytes cover pos, which is the largest index with dst <= pos
             return r0;
         }
-        int64_t lo = 0, hi = a.nreq; // 32-ary search across the lanes, shared-memory reads
+        int64_t lo = 0, hi = nreq; // 32-ary search across the lanes, shared-memory reads
         while (hi - lo > 1) {
             int64_t step = (hi - lo + 31) / 32;
             int64_t idx = lo + (int64_t)(lane + 1) * step;
@@ -460,7 +515,7 @@ struct ChunkWalker {
                 seg_end = min(T, seg_pos + seg_bytes);
                 r = FIXED ? seg_pos / nb : locate_var(a, seg_pos, lane);
             }
-            if (r >= a.nreq) { // defensive: cannot happen while seg_pos < T
+            if (r >= nreq) { // defensive: cannot happen while seg_pos < T
                 seg_pos = seg_end;
                 continue;
             }
@@ -490,7 +545,7 @@ struct ChunkWalker {
             const int64_t q_d0 = __shfl_sync(0xffffffffu, w_dst, srcl & 31);
             const int64_t q_n = __shfl_sync(0xffffffffu, w_n, srcl & 31);
             const int64_t q_end = q_d0 + q_n;
-            const bool valid = srcl < 32 && r + lane < a.nreq && q_d0 < seg_end;
+            const bool valid = srcl < 32 && r + lane < nreq && q_d0 < seg_end;
             const int64_t p0 = max(q_d0, seg_pos);
             int64_t len = min(q_end, seg_end) - p0;
             len = max(len, (int64_t)0);
@@ -674,6 +729,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     __shared__ __align__(8) uint64_t full_bar[NW][S];
     __shared__ __align__(16) PieceDesc desc[NW][S][32];
     __shared__ int64_t wtot[PCAP > 0 ? NW : 1];
+    __shared__ int64_t push_rbase[FIXED ? DDSK_MAX_RANKS + 1 : 1];
+    __shared__ uint64_t push_win[FIXED ? DDSK_MAX_RANKS : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -751,6 +808,66 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         }
     }
 
+    // ---- collective owner-push fetch: publish my list, wait for everybody's, build the requester table -------------
+    // Protocol (one launch per rank per step t, every rank on its own GPU):
+    //   1. this rank's index list is copied into its window (list [t & 1]) by a memcpy queued in front of the launch;
+    //      CTA 0 publishes ready = t;
+    //   2. every warp waits until every rank's ready >= t (words polled over NVLink, system scope);
+    //   3. the walk below runs over the CONCATENATION of all lists; a request is acted on only by its owner, which
+    //      TMA-loads the rows from its own HBM and TMA-stores them into the requester's window (posted NVLink writes);
+    //   4. the last warp of the grid tells every requester "owner `me`: rows of step t have landed" (after its stores
+    //      were performed and fenced at system scope) and then waits for the same word from every owner in its own
+    //      window, so the kernel ends only when this rank's batch is complete.
+    // A window's list / buffer [t & 1] is reused at step t + 2: this rank's kernel t + 2 starts after its kernel t
+    // ended, i.e. after every owner finished reading list t (they signalled arrival after their last read).
+    // CTA 0 never waits for another CTA of its own grid, and CTAs are dispatched in index order, so the only waits are
+    // on other GPUs' kernels -- which every rank launches (the call is collective).
+    const bool push = FIXED && a.push != nullptr;
+    if (FIXED && push) {
+        const ddsk_push_t *ps = a.push;
+        const int P = ps->nranks, me = ps->me, par = (int)(a.push_step & 1ull);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { // (the list itself was copied into the window by a stream-ordered
+                                                    // memcpy in front of this launch: ddsk_gather_push)
+            unsigned long long *hdr = (unsigned long long *)ps->win[me];
+            *(volatile unsigned long long *)&hdr[1 + par] = (unsigned long long)a.push_nreq;
+            __threadfence_system();
+            st_release_sys_u64(&hdr[0], a.push_step);
+        }
+        const uint64_t t0 = globaltimer_ns();
+        for (int r0 = 0; r0 < P; r0 += 32) {
+            const int r = r0 + lane;
+            while (r < P && ld_acquire_sys_u64((const unsigned long long *)ps->win[r]) < a.push_step) {
+                __nanosleep(200);
+                if (globaltimer_ns() - t0 > 30000000000ull) { // 30 s: a rank that never launched must not hang the box
+                    report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+        if (warp == 0) {
+            int64_t n = 0;
+            for (int r0 = 0; r0 < P; r0 += 32) { // (P <= 64: at most two rounds)
+                const int r = r0 + lane;
+                int64_t mine_n = 0;
+                if (r < P) {
+                    push_win[r] = (uint64_t)ps->win[r];
+                    mine_n = ld_relaxed_sys_s64((const int64_t *)ps->win[r] + 1 + par);
+                }
+                const int64_t incl = warp_incl_scan(mine_n, lane);
+                if (r < P) push_rbase[r] = n + incl - mine_n;
+                n += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) push_rbase[P] = n;
+        }
+        __syncthreads();
+        w.push_n = P;
+        w.push_me = me;
+        w.push_par = par;
+        w.push_rbase = push_rbase;
+        w.push_win = push_win;
+        w.push_idx_off = ps->idx_off[par];
+    }
     if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
     bool dbg_first = a.dbg != nullptr && warp == 0;
     // ---- total bytes, segment geometry -------------------------------------------------------
@@ -759,8 +876,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     w.static_claims = a.tickets == nullptr;
     if (a.overlap && a.tickets) pass_gate(); // the slot's ticket word was last used by launch q-4
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
-    if (FIXED) w.T = w.nb * a.nreq;
+    w.nreq = (FIXED && push) ? push_rbase[w.push_n] : a.nreq;
+    if (FIXED) w.T = w.nb * w.nreq;
     bool over = w.T > a.dst_cap;
+    const int64_t push_dst_off = (FIXED && push) ? a.push->dst_off[w.push_par] : 0;
     // multi-array batch: the walk runs over the concatenation of the variables' packed results; vbase[v] is where
     // variable v starts in that virtual space (unused slots are +inf so dst_of() never selects them)
     const bool multi = !FIXED && a.plan.nvars > 1;
@@ -781,6 +900,12 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         if (PCAP > 0) over |= w.T > 0xFFFFFFFFll; // 32-bit shared offsets
     }
     auto dst_of = [&](int64_t dpos) -> char * {
+        if (FIXED && push) { // the requester's window, found from the position in the concatenated packed space
+            int p = 0;
+            for (int k = 1; k < w.push_n; k++)
+                if (dpos >= push_rbase[k] * w.nb) p = k;
+            return (char *)push_win[p] + push_dst_off + (dpos - push_rbase[p] * w.nb);
+        }
         if (!multi) return a.dst + dpos;
         int64_t b = vbase[0]; // static indices only: the tables stay in registers / the constant bank
         char *d = a.mdst[0];
@@ -796,6 +921,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         // A claim is one atomic (requested ahead of need) + a division (FIXED), a shared-memory search (VAR, plan in
         // shared memory) or one global load (VAR, plan in global scratch). Small segments (8 per warp) keep the tail
         // short; variable-count segments are multiples of SEG_GRAIN when the segment table is in use.
+        // (push fetch: finer segments were measured WORSE -- 304 vs 270 us per step at N=2 -- because every claim costs a
+        // window of index reads from the requester's list over NVLink)
         int64_t target = w.T / (nwarps * 8);
         const int64_t unit = (!FIXED && PCAP == 0) ? SEG_GRAIN : (int64_t)CH;
         target = max((int64_t)a.min_seg_chunks * CH, min(target, (int64_t)1 << 20));
@@ -813,7 +940,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
 
     // ---- FIXED with nothing to walk (count <= 0, or the batch does not fit): run the reference's two checks here,
     //      so an invalid request is still the error that gets reported
-    if (FIXED && (w.nb <= 0 || over)) {
+    if (FIXED && !push && (w.nb <= 0 || over)) {
         for (int64_t i = gwarp * 32 + lane; i < a.nreq; i += nwarps * 32) {
             uint64_t s;
             int code = dev_locate(a.var, a.starts[i], a.count, &s);
@@ -892,8 +1019,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         __syncwarp();  // all lanes are done reading the stage before it is refilled
         consumed++;
     }
-    if (a.overlap) {
-        bulk_wait_all<0>(); // every lane: its bulk stores have been performed (the done word below promises that)
+    if (a.overlap || (FIXED && push)) {
+        bulk_wait_all<0>(); // every lane: its bulk stores have been performed (the done / arrive word below promises that)
         fence_proxy_async_global();
     } else {
         bulk_wait_read<0>(); // every lane: its stages have been read out; the global writes complete with the grid
@@ -912,7 +1039,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             }
         }
     }
-    if (FIXED && a.offsets_out) { // arithmetic offsets, written off the critical path
+    if (FIXED && a.offsets_out && !push) { // arithmetic offsets, written off the critical path
         for (int64_t i = gwarp * 32 + lane; i <= a.nreq; i += nwarps * 32) a.offsets_out[i] = i * w.nb;
     }
 
@@ -933,12 +1060,31 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         }
     } else if (lane == 0) {
         // ---- self-resetting ticket counters
-        __threadfence();
+        if (FIXED && push) __threadfence_system(); else __threadfence();
         unsigned int done = atomicAdd(&a.counters[1], 1u);
         if (done == (unsigned int)(nwarps - 1)) {
             a.counters[0] = 0;
             a.counters[1] = 0;
             __threadfence();
+            if (FIXED && push) {
+                // every warp of this rank has pushed and fenced: tell the requesters, then wait for my own owners
+                const ddsk_push_t *ps = a.push;
+                for (int r = 0; r < ps->nranks; r++)
+                    st_release_sys_u64((unsigned long long *)ps->win[r] + 8 + ps->me, a.push_step);
+                const unsigned long long *hdr = (const unsigned long long *)ps->win[ps->me];
+                const uint64_t t0 = globaltimer_ns();
+                for (int r = 0; r < ps->nranks; r++)
+                    while (ld_acquire_sys_u64(&hdr[8 + r]) < a.push_step) {
+                        __nanosleep(200);
+                        if (globaltimer_ns() - t0 > 30000000000ull) {
+                            report(a.status, a.nreq, DDSK_CODE_WATCHDOG);
+                            __trap();
+                        }
+                    }
+                // errors the owners found in MY requests sit in my window's status word
+                const unsigned long long st = *(volatile const unsigned long long *)&hdr[3];
+                if (st != DDSK_STATUS_OK) atomicMin(a.status, st);
+            }
             if (a.host_mirror) { // the last warp publishes status + total straight into pinned host memory: the host
                                  // reads them after the stream sync, no D2H copy in the call
                 a.host_mirror[0] = *(volatile unsigned long long *)a.status;
@@ -1516,6 +1662,33 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
     a.min_seg_chunks = 1;
     fill_overlap(a, scr, flags);
     a.host_mirror = (flags & DDSK_F_MIRROR) ? scr->host_mirror : nullptr;
+    return launch_gather<true>(a, st);
+}
+
+int ddsk_gather_push(const ddsk_var_t *var, const ddsk_push_t *push_host, const ddsk_push_t *push_dev,
+                     const int64_t *starts_dev, int64_t count, int64_t nreq, unsigned long long step,
+                     const ddsk_scratch_t *scr, unsigned int *push_counters, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = pick_geometry()) return rc;
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.var = *var;
+    a.count = count;
+    a.nreq = nreq; // (this rank's own requests; the walk covers every rank's)
+    a.dst = nullptr;
+    a.dst_cap = INT64_MAX;
+    a.status = scr->status;
+    a.counters = scr->counters;
+    a.tickets = scr->counters;
+    a.min_seg_chunks = 1;
+    a.push = push_dev;
+    if (nreq > 0) // this rank's list into its window, stream-ordered before the kernel that publishes it
+        CUDA_TRY(cudaMemcpyAsync(push_host->win[push_host->me] + push_host->idx_off[step & 1ull], starts_dev, (size_t)nreq * 8,
+                                 cudaMemcpyDeviceToDevice, st));
+    a.push_src_idx = starts_dev;
+    a.push_nreq = nreq;
+    a.push_step = step;
+    a.push_counters = push_counters;
     return launch_gather<true>(a, st);
 }
 

@@ -105,6 +105,24 @@ typedef struct ddsk_multi {
 int ddsk_gather_multi(const ddsk_multi_t *m, const int64_t *sample_ids_dev, int64_t nreq, ddsk_scratch_t *scr, int flags,
                       void *stream);
 
+/* Collective owner-push fetch (fixed-count batches, every rank on its own GPU). Each rank owns a WINDOW -- a peer-mapped
+ * block of the store -- holding a header, two index lists and two destination buffers (alternating by step parity).
+ * Header, as 64-bit words: [0] ready (the step whose index list is published), [1 + parity] number of requests,
+ * [3] sticky status (atomicMin, written by the owners), [8 + r] arrive (the step for which owner r's rows have landed). */
+#define DDSK_PUSH_HDR_BYTES 4096
+typedef struct ddsk_push {
+    int32_t nranks, me;
+    unsigned char *win[DDSK_MAX_RANKS]; /* rank r's window as mapped into this process */
+    int64_t idx_off[2], dst_off[2];     /* byte offsets inside a window */
+    int64_t max_requests, max_bytes;
+} ddsk_push_t;
+/* One step of the collective fetch: publish this rank's `nreq` start rows (device array), wait for every rank's list,
+ * push the rows THIS rank owns into the requesters' windows, wait until every owner's rows have landed here.
+ * push_host / push_dev: the table above and its device copy; counters: 1 zeroed device word. Result: window dst buffer [step & 1]. */
+int ddsk_gather_push(const ddsk_var_t *var, const ddsk_push_t *push_host, const ddsk_push_t *push_dev,
+                     const int64_t *starts_dev, int64_t count, int64_t nreq, unsigned long long step,
+                     const ddsk_scratch_t *scr, unsigned int *push_counters, void *stream);
+
 /* One request in a 1-CTA kernel (the legacy per-sample get()): checks + copy into `dst` (device memory or mapped pinned
  * host memory), then flag[0] = status word, flag[1] = bytes, flag[2] = ticket (flag = mapped pinned host words). */
 int ddsk_small_get(const ddsk_var_t *var, int64_t start, int64_t count, void *dst, int64_t dst_capacity,

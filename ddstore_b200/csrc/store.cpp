@@ -250,6 +250,15 @@ struct dds_store {
     bool db_alive = false, db_enabled = true;
     std::set<cudaStream_t> update_streams; // caller streams that carried dds_update_async copies since the last fence
     IngestPool *ingest = nullptr;
+    // collective owner-push fetch: the windows are an internal byte variable of the store (so the ordinary shard
+    // machinery allocates, exports and maps them on every rank)
+    struct Push {
+        bool ready = false;
+        ddsk_push_t table;
+        ddsk_push_t *d_table = nullptr;
+        unsigned int *d_counters = nullptr;
+        unsigned long long step = 0;
+    } push;
 };
 
 namespace {
@@ -703,6 +712,8 @@ int decode_status_word(unsigned long long st, int64_t *bad_index) {
 // The device status word is sticky (kernels only atomicMin into it): re-arm it after an error was read.
 int decode_status(dds_store *s, cudaStream_t stream, unsigned long long st, int64_t *bad_index) {
     if (st != DDSK_STATUS_OK) {
+        if (s->push.ready) // the owners report errors of a pushed batch into this rank's window
+            cudaMemsetAsync(s->push.table.win[s->push.table.me] + 24, 0xFF, 8, stream);
         cudaMemsetAsync(s->scr.status, 0xFF, 8, stream);
         cudaStreamSynchronize(stream);
     }
@@ -1423,6 +1434,94 @@ int dds_get(dds_store_t *s, const char *name, int64_t start, int64_t count, int 
                          buffer_on_device ? DDS_DST_ON_DEVICE : 0u, nullptr, nullptr, nullptr);
 }
 
+static const char *kPushWindow = "\001dds-push-window";
+
+int dds_push_setup(dds_store_t *s, int64_t max_requests, int64_t max_bytes) {
+    clear_error();
+    if (!s) return fail(DDS_ERR_ARG, "null store");
+    if (s->push.ready) return fail(DDS_ERR_EXISTS, "push windows");
+    int rc_local = DDS_OK;
+    if (max_requests <= 0 || max_bytes <= 0) rc_local = fail(DDS_ERR_ARG, "push windows need positive sizes");
+    // every rank must sit on a GPU of its own: a rank's kernel waits for the other ranks' kernels to run
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), s->device) != cudaSuccess) bus[0] = 0;
+    (void)cudaGetLastError();
+    struct Rec {
+        char bus[32];
+        int64_t max_requests, max_bytes;
+        int32_t ok, pad_;
+    } mine;
+    memset(&mine, 0, sizeof(mine));
+    memcpy(mine.bus, bus, sizeof(bus));
+    mine.max_requests = max_requests;
+    mine.max_bytes = max_bytes;
+    mine.ok = rc_local == DDS_OK;
+    std::vector<Rec> all((size_t)s->size);
+    if (int rc = dds_comm_allgather(s->comm, &mine, all.data(), sizeof(Rec))) return rc;
+    bool bad = false, shared = false, differ = false;
+    for (int a = 0; a < s->size; a++) {
+        bad |= !all[(size_t)a].ok;
+        differ |= all[(size_t)a].max_requests != max_requests || all[(size_t)a].max_bytes != max_bytes;
+        for (int b = a + 1; b < s->size; b++) shared |= memcmp(all[(size_t)a].bus, all[(size_t)b].bus, sizeof(mine.bus)) == 0;
+    }
+    if (bad) return rc_local ? rc_local : fail(DDS_ERR_ARG, "a peer rank passed bad push window sizes");
+    if (differ) return fail(DDS_ERR_ARG, "every rank must pass the same push window sizes");
+    if (shared) return fail(DDS_ERR_ARG, "the collective push fetch needs every rank on a GPU of its own");
+    auto up = [](int64_t v) { return (v + 4095) / 4096 * 4096; };
+    ddsk_push_t &t = s->push.table;
+    memset(&t, 0, sizeof(t));
+    t.nranks = s->size;
+    t.me = s->rank;
+    t.max_requests = max_requests;
+    t.max_bytes = max_bytes;
+    t.idx_off[0] = DDSK_PUSH_HDR_BYTES;
+    t.idx_off[1] = t.idx_off[0] + up(max_requests * 8);
+    t.dst_off[0] = t.idx_off[1] + up(max_requests * 8);
+    t.dst_off[1] = t.dst_off[0] + up(max_bytes);
+    const int64_t bytes = t.dst_off[1] + up(max_bytes);
+    if (int rc = register_var(s, kPushWindow, nullptr, bytes, 1, 1, 0, true)) return rc; // collective, zero-filled, mapped
+    Var *w = find_var(s, kPushWindow);
+    for (int r = 0; r < s->size; r++) t.win[r] = (unsigned char *)w->kv.bases[r];
+    CU(cudaMemset(t.win[t.me] + 24, 0xFF, 8)); // the window's status word starts as "ok"
+    CU(cudaMalloc((void **)&s->push.d_table, sizeof(ddsk_push_t)));
+    CU(cudaMemcpy(s->push.d_table, &t, sizeof(t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&s->push.d_counters, 16));
+    CU(cudaMemset(s->push.d_counters, 0, 16));
+    s->push.step = 0;
+    if (int rc = dds_comm_barrier(s->comm)) return rc; // every window is armed before anyone pushes
+    s->push.ready = true;
+    return DDS_OK;
+}
+
+int dds_get_batch_push(dds_store_t *s, const char *name, const int64_t *starts_dev, int64_t fixed_count, int64_t nreq,
+                       int itemsize, void **dst_out, void *cuda_stream) {
+    clear_error();
+    if (!s || !dst_out) return fail(DDS_ERR_ARG, "null store or dst_out");
+    if (!s->push.ready) return fail(DDS_ERR_ARG, "no push windows (call dds_push_setup on every rank first)");
+    Var *v = find_var(s, name);
+    if (!v) return fail(DDS_ERR_UNKNOWN_VAR, name ? name : "(null)");
+    if (v->itemsize != itemsize) return fail(DDS_ERR_DTYPE);
+    const int64_t nb = fixed_count * v->kv.row_bytes;
+    if (fixed_count <= 0 || nreq < 0 || (nreq > 0 && !starts_dev)) return fail(DDS_ERR_ARG, "push batches fetch count >= 1 rows per request");
+    if (nreq > s->push.table.max_requests || nreq * nb > s->push.table.max_bytes)
+        return fail(DDS_ERR_CAPACITY, "batch larger than the push window");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    if (s->pending && st != s->pending_stream) {
+        if (int rc = dds_batch_wait(s, nullptr, nullptr)) return rc;
+    }
+    s->run_len = 0;
+    const unsigned long long step = ++s->push.step;
+    if (ddsk_gather_push(&v->kv, &s->push.table, s->push.d_table, starts_dev, fixed_count, nreq, step, &s->scr, s->push.d_counters, st))
+        return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
+    *dst_out = s->push.table.win[s->push.table.me] + s->push.table.dst_off[step & 1ull];
+    s->pending = true; // dds_batch_wait reports what the owners found wrong with this rank's requests
+    s->pending_stream = st;
+    s->pending_fixed_total = nreq * nb;
+    s->pending_nreq = nreq;
+    return DDS_OK;
+}
+
 int dds_query(dds_store_t *s, const char *name, dds_varinfo_t *out) {
     clear_error();
     if (!s || !out) return fail(DDS_ERR_ARG, "null store or out");
@@ -1492,6 +1591,9 @@ int dds_free(dds_store_t *s) {
     s->zombies.clear();
     s->zombie_blocks.clear();
     s->multi_key.clear();
+    if (s->push.d_table) cudaFree(s->push.d_table);
+    if (s->push.d_counters) cudaFree(s->push.d_counters);
+    s->push = dds_store::Push();
     return rc ? rc : rc2;
 }
 
@@ -1544,6 +1646,8 @@ void dds_destroy(dds_store_t *s) {
         if (s->d_vars) cudaFree(s->d_vars);
         if (s->db_stream) cudaStreamDestroy(s->db_stream);
         if (s->d_multi_vars) cudaFree(s->d_multi_vars);
+        if (s->push.d_table) cudaFree(s->push.d_table);
+        if (s->push.d_counters) cudaFree(s->push.d_counters);
         if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();

@@ -50,6 +50,13 @@ class _Buf:
         self.nbytes = self.size * self.itemsize
 
 
+class _DevMem:
+    """a raw device range as a __cuda_array_interface__ object (uint8)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 def _i64(x):
     """host int64 contiguous ndarray view of an index list/array"""
     return np.ascontiguousarray(x, dtype=np.int64)
@@ -67,6 +74,7 @@ class PyDDStore:
         self.rank, self.size = self._L.dds_rank(self._h), self._L.dds_size(self._h)
         self._itemsize = {}  # per-variable itemsize, cached for the hot path
         self._cname = {}     # name -> bytes, cached for the per-sample get() loop
+        self._rowbytes = {}
         self.last_bad_index = -1
 
     # ---------------------------------------------------------------- reference surface
@@ -187,6 +195,30 @@ class PyDDStore:
         self.last_bad_index = bad.value
         _capi.raise_for(rc)
         return total.value
+
+    # ---------------------------------------------------------------- collective owner-push fetch
+    def push_setup(self, max_requests, max_bytes):
+        """COLLECTIVE: allocate and peer-map the windows of the push fetch (see dds_push_setup)."""
+        _capi.raise_for(self._L.dds_push_setup(self._h, int(max_requests), int(max_bytes)))
+
+    def get_batch_push(self, name, starts, count=1, stream=None):
+        """COLLECTIVE fetch of len(starts) requests (CUDA int64 tensor) of `count` rows each, by owner-push. Returns a
+        uint8 CUDA tensor VIEW of the packed rows inside this rank's window (valid until the next-but-one push step);
+        the step is enqueued on `stream`, wait() reports errors."""
+        import torch
+        itemsize = self._itemsize.get(name)
+        if itemsize is None:
+            itemsize = self._itemsize[name] = self.query(name)["itemsize"]
+        if not (hasattr(starts, "data_ptr") and starts.is_cuda):
+            raise ValueError("get_batch_push takes a CUDA int64 tensor of start rows")
+        out = C.c_void_p()
+        _capi.raise_for(self._L.dds_get_batch_push(self._h, name.encode(), starts.data_ptr(), int(count), starts.numel(), itemsize,
+                                                   C.byref(out), self._stream_arg(stream)))
+        rb = self._rowbytes.get(name)
+        if rb is None:
+            rb = self._rowbytes[name] = self.query(name)["disp"] * itemsize
+        nbytes = starts.numel() * int(count) * rb
+        return torch.as_tensor(_DevMem(out.value or 0, nbytes), device=starts.device)
 
     # ---------------------------------------------------------------- per-sample index (variable-length datasets)
     def set_sample_index(self, name, row_start, row_count):

@@ -171,6 +171,20 @@ int dds_get_samples_multi(dds_store_t *s, int nvars, const char *const *names, c
                           void *const *dsts, const int64_t *dst_capacities, int64_t *const *dst_offsets, unsigned flags,
                           void *cuda_stream, int64_t *total_bytes, int64_t *bad_index);
 
+/* COLLECTIVE fetch by owner-PUSH (every rank calls, every rank on a GPU of its own; fixed-count batches). A one-sided
+ * get() pulls: every NVLink direction then carries payload + response headers + the read requests of the opposite
+ * flow (1.31 link bytes per payload byte, counters in profiles/r2_nvlink_counters.md). When all ranks fetch in the same
+ * step anyway -- a DDP loader -- the owners can push instead (posted writes, +6 % payload per link): each rank
+ * publishes its start rows in its WINDOW, every owner sends the rows it owns straight into the requesters' windows and
+ * signals arrival; the call's kernel ends when this rank's batch is complete. dds_push_setup allocates and maps the
+ * windows (room for max_requests start rows and max_bytes of packed rows, twice: results alternate between two
+ * buffers, so the buffer returned for step t stays valid until step t + 2). dds_get_batch_push enqueues one step on
+ * cuda_stream and returns the device address the packed rows will be at; dds_batch_wait reports errors (same texts
+ * and first-bad index as dds_get_batch). */
+int dds_push_setup(dds_store_t *s, int64_t max_requests, int64_t max_bytes);
+int dds_get_batch_push(dds_store_t *s, const char *name, const int64_t *starts_dev, int64_t fixed_count, int64_t nreq,
+                       int itemsize, void **dst_out, void *cuda_stream);
+
 /* Completes the batch issued with DDS_NO_SYNC (stream sync + status decode). */
 int dds_batch_wait(dds_store_t *s, int64_t *total_bytes, int64_t *bad_index);
 

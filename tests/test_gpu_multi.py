@@ -108,3 +108,75 @@ def test_one_process_per_gpu_cuda_ipc(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ipc-ok {r}" in o, f"rank {r}:\n{o[-3000:]}"
+
+
+def test_collective_push_fetch_matches_pull(coracle):
+    """dds_get_batch_push (every rank publishes its start rows, every OWNER pushes its rows into the requesters'
+    windows over NVLink): byte for byte the rows the one-sided pull delivers, for several steps (the windows' two
+    buffers alternate), different batch sizes per rank, multi-row requests, 4-byte-phase rows; an invalid request is
+    reported to the REQUESTER with its index and the reference's text; thread-ranks sharing a GPU are refused."""
+    import torch
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    P = min(n, 4)
+    rng = np.random.default_rng(4242)
+    for dtype, disp, count in ((np.float32, 1024, 1), (np.float32, 3, 5), (np.uint8, 7, 2)):
+        nrows, shards = random_world(rng, P, dtype, disp, max_rows=6000, allow_empty=False)
+        ll = O.np_lenlist(nrows)
+        steps = 5
+        reqs = [[random_valid_requests(rng, ll, 1500 + 301 * r + 17 * t, max_count=count)[0] for t in range(steps)] for r in range(P)]
+        for r in range(P):  # keep every request of `count` rows inside its owner
+            for t in range(steps):
+                s = reqs[r][t]
+                own = np.searchsorted(ll, s, side="right")
+                s[:] = np.minimum(s, ll[own] - count)
+                lo = np.concatenate([[0], ll])[own]
+                s[:] = np.maximum(s, lo)
+        row = disp * np.dtype(dtype).itemsize
+
+        def body(store, r):
+            dev = torch.device("cuda", r)
+            torch.cuda.set_device(r)
+            store.add("v", shards[r])
+            store.push_setup(4000, 4000 * count * row)
+            st = torch.cuda.Stream(device=dev)
+            for t in range(steps):
+                ids = torch.from_numpy(reqs[r][t]).to(dev)
+                torch.cuda.synchronize(dev)
+                got = store.get_batch_push("v", ids, count=count, stream=st.cuda_stream)
+                store.wait()
+                exp, _, bad, _ = coracle.get_batch(shards, reqs[r][t], np.full(len(reqs[r][t]), count))
+                assert bad == -1 and got.cpu().numpy().tobytes() == exp.tobytes(), (r, t)
+                pull = torch.zeros(exp.size, dtype=torch.uint8, device=dev)
+                store.get_batch("v", ids, out=pull, count=count)
+                assert torch.equal(pull, got)
+            # rank 1 asks for a row that does not exist: only rank 1 sees the error, at the right index
+            ids = torch.from_numpy(reqs[r][0]).to(dev).clone()
+            if r == 1:
+                ids[77] = int(ll[-1])
+            torch.cuda.synchronize(dev)
+            store.get_batch_push("v", ids, count=count, stream=st.cuda_stream)
+            if r == 1:
+                with pytest.raises(ValueError, match="Invalid count on target"):
+                    store.wait()
+                assert store.last_bad_index == 77
+            else:
+                store.wait()
+            ids = torch.from_numpy(reqs[r][1]).to(dev)
+            torch.cuda.synchronize(dev)
+            got = store.get_batch_push("v", ids, count=count, stream=st.cuda_stream)  # the step after an error works
+            store.wait()
+            exp, _, _, _ = coracle.get_batch(shards, reqs[r][1], np.full(len(reqs[r][1]), count))
+            assert got.cpu().numpy().tobytes() == exp.tobytes()
+            return True
+
+        assert all(run_world(P, body, devices=list(range(P))))
+
+    def shared(store, r):
+        store.add("v", np.zeros((10, 4), np.float32))
+        with pytest.raises(ValueError, match="GPU of its own"):
+            store.push_setup(16, 4096)
+        return True
+
+    assert all(run_world(2, shared, devices=[0, 0]))
