@@ -890,6 +890,33 @@ int dds_update_async(dds_store_t *s, const char *name, const void *buffer, int64
                        cuda_stream ? (cudaStream_t)cuda_stream : (s ? s->stream : nullptr), false);
 }
 
+// the staging pool shared by dds_ingest (pageable -> shard) and large pageable destinations (staging buffer -> pageable)
+static int ensure_pool(dds_store_t *s) {
+    if (s->ingest) return DDS_OK;
+    IngestPool *p = new IngestPool;
+    bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; k++)
+        ok = cudaHostAlloc((void **)&p->pin[k], IngestPool::kStage, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaError_t e = cudaGetLastError();
+        for (int k = 0; k < 2; k++) {
+            if (p->pin[k]) cudaFreeHost(p->pin[k]);
+            if (p->ev[k]) cudaEventDestroy(p->ev[k]);
+        }
+        if (p->stream) cudaStreamDestroy(p->stream);
+        delete p;
+        return cuda_fail(e, "staging pool setup");
+    }
+    int nt = 6;
+    if (const char *e = getenv("DDS_INGEST_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof(cs), &cs) == 0) nt = std::max(1, std::min(nt, CPU_COUNT(&cs)));
+    p->start(nt);
+    s->ingest = p;
+    return DDS_OK;
+}
+
 int dds_ingest(dds_store_t *s, const char *name, const void *host_rows, int64_t nrows, int64_t offset, int itemsize) {
     // update<T> (ddstore.hpp:181-195) for a chunk of PAGEABLE host rows, pipelined: parallel CPU copy into pinned staging
     // buffers + async H2D. Returns once the source has been consumed (the caller may reuse it); the last copies complete
@@ -906,29 +933,7 @@ int dds_ingest(dds_store_t *s, const char *name, const void *host_rows, int64_t 
     if (total == 0) return DDS_OK;
     if (!host_rows) return fail(DDS_ERR_ARG, "null buffer");
     CU(cudaSetDevice(s->device));
-    if (!s->ingest) {
-        IngestPool *p = new IngestPool;
-        bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; k++)
-            ok = cudaHostAlloc((void **)&p->pin[k], IngestPool::kStage, cudaHostAllocDefault) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) {
-            cudaError_t e = cudaGetLastError();
-            for (int k = 0; k < 2; k++) {
-                if (p->pin[k]) cudaFreeHost(p->pin[k]);
-                if (p->ev[k]) cudaEventDestroy(p->ev[k]);
-            }
-            if (p->stream) cudaStreamDestroy(p->stream);
-            delete p;
-            return cuda_fail(e, "dds_ingest: staging setup");
-        }
-        int nt = 6;
-        if (const char *e = getenv("DDS_INGEST_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
-        cpu_set_t cs;
-        if (sched_getaffinity(0, sizeof(cs), &cs) == 0) nt = std::max(1, std::min(nt, CPU_COUNT(&cs)));
-        p->start(nt);
-        s->ingest = p;
-    }
+    if (int rc = ensure_pool(s)) return rc;
     IngestPool *p = s->ingest;
     const char *src = (const char *)host_rows;
     char *dst = (char *)v->base + (size_t)offset * row;
@@ -950,6 +955,45 @@ int dds_ingest(dds_store_t *s, const char *name, const void *host_rows, int64_t 
     }
     s->update_streams.insert(p->stream); // the next fence / free waits for the tail
     return DDS_OK;
+}
+
+// A packed batch from the store's HBM staging buffer into a PAGEABLE host destination (the reference's np.zeros
+// contract, examples/vae/distdataset.py:80-85): cudaMemcpyAsync into pageable memory is staged by the driver through
+// one thread (20.7 GB/s measured); here the copy engine fills the pool's pinned buffers chunk by chunk while the
+// worker threads copy the previous chunk out. `st` has the gather queued; synchronous.
+static int d2h_pageable(dds_store_t *s, void *dst, const void *d_src, size_t bytes, cudaStream_t st) {
+    if (int rc = ensure_pool(s)) return rc;
+    IngestPool *p = s->ingest;
+    for (int k = 0; k < 2; k++)
+        if (p->ev_pending[k]) { // an ingest still owns the staging buffers
+            CU(cudaEventSynchronize(p->ev[k]));
+            p->ev_pending[k] = false;
+        }
+    const size_t step = IngestPool::kStage;
+    const size_t nchunks = (bytes + step - 1) / step;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t off = c * step, n = std::min(step, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(p->pin[c & 1], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(p->ev[c & 1], st);
+        return e;
+    };
+    CU(issue(0));
+    for (size_t c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) CU(issue(c + 1)); // (its buffer was emptied by the CPU copy of chunk c - 1, below)
+        CU(cudaEventSynchronize(p->ev[c & 1]));
+        const size_t off = c * step, n = std::min(step, bytes - off);
+        p->copy((char *)dst + off, p->pin[c & 1], n);
+    }
+    return DDS_OK;
+}
+
+static bool is_pageable(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 int dds_ingest_wait(dds_store_t *s) {
@@ -1240,7 +1284,11 @@ static int batch_impl(dds_store_t *s, Var *v, bool by_sample, const int64_t *sta
             if (tot > cap) tot = cap;
             if (tot > 0) memcpy(dst, s->h_small + kSmallIdx * 16, (size_t)tot); // pinned bounce -> the caller's buffer
         } else if (upper >= 0) {
-            if (cap > 0) CU(cudaMemcpyAsync(dst, d_dst, (size_t)cap, cudaMemcpyDeviceToHost, st));
+            if (cap >= (int64_t)(4u << 20) && is_pageable(dst)) {
+                if (int rc = d2h_pageable(s, dst, d_dst, (size_t)cap, st)) return rc;
+            } else if (cap > 0) {
+                CU(cudaMemcpyAsync(dst, d_dst, (size_t)cap, cudaMemcpyDeviceToHost, st));
+            }
         } else {
             CU(cudaStreamSynchronize(st)); // device-resident counts: the size is only known on the device
             int64_t tot = (int64_t)s->h_status[1];
