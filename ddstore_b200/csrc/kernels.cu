@@ -345,7 +345,7 @@ struct GatherArgs {
     int min_seg_chunks;                // smallest segment, in chunks (claims cost more when the plan is in global memory)
     // ---- overlap protocol (DDS_OVERLAP: a batch declared independent of the ONE batch queued right before it)
     //   * fixed-count launches stride their segments statically; variable-count launches (whose CTAs may start late,
-    //     behind the plan kernels) claim them by ticket from a word of their own slot, after passing the gate below;
+    //     behind the plan kernel) claim them by ticket from a word of their own slot, armed once the gate below is open;
     //   * launch q of a run may start while q-1 is still running (skip_wait: no griddepcontrol.wait), but
     //     - it does not write a byte of caller-visible memory before launch q-2 has RETIRED (gate on done[q-2]):
     //       a double-buffered queue that reuses the buffers of batch q-2 is safe whatever else occupies the GPU;
@@ -416,6 +416,8 @@ struct ChunkWalker {
     bool first_claim = true, static_claims = false;
     int64_t cur_seg = 0;
     unsigned int pend = 0; // lane 0: ticket claimed ahead of need (the atomic's latency hides behind the current segment)
+    bool armed = false;    // a ticket has been requested and not yet consumed
+    bool gate_ok = true;   // the ticket word may be touched (overlap launches: only once launch q-2 has retired)
     int64_t r = 0, win_base = -64;
     int64_t nreq = 0; // requests of the walk (a.nreq; the sum over all requesters in a collective push fetch)
     // collective push fetch: the walk runs over the concatenation of every requester's list
@@ -491,23 +493,36 @@ struct ChunkWalker {
     }
 
     // Next group of the walk. Returns the bytes to expect in the stage (0: no more work); `pc` is this lane's piece.
-    template <int STAGE>
-    __device__ __forceinline__ uint32_t next_group(const GatherArgs &a, int lane, Piece &pc) {
+    __device__ __forceinline__ void arm(const GatherArgs &a, int lane) { // request the ticket of the NEXT segment
+        if (lane == 0) pend = atomicAdd(a.tickets, 1u);
+        armed = true;
+    }
+
+    template <int STAGE, typename Gate>
+    __device__ __forceinline__ uint32_t next_group(const GatherArgs &a, int lane, Piece &pc, Gate &&gate) {
         while (true) {
             if (seg_pos >= seg_end) {
                 // the first segment of warp g is segment g (no ticket: spares ~1800 same-address atomics at the
                 // start of every launch); later ones come from the ticket counter, offset by the warp count. The
-                // ticket for the segment AFTER this one is requested now and read at the next claim.
+                // ticket for the segment AFTER this one is requested ahead of need and read at the next claim. In an
+                // overlap launch the ticket word belongs to the launch's slot and may only be touched once the gate
+                // is open (its previous user has retired): normally that happens at this warp's first drain.
                 int64_t seg;
                 if (first_claim) {
                     first_claim = false;
                     seg = gwarp;
-                    if (!static_claims && seg < nseg && lane == 0) pend = atomicAdd(a.tickets, 1u);
+                    if (!static_claims && seg < nseg && gate_ok) arm(a, lane);
                 } else if (static_claims) {
-                    seg = cur_seg + nwarps; // overlapped launches share no mutable state: plain striding
+                    seg = cur_seg + nwarps; // no ticket word at all: plain striding
                 } else {
+                    if (!armed) { // (first segment exhausted before the first drain: open the gate here)
+                        gate();
+                        gate_ok = true;
+                        arm(a, lane);
+                    }
                     seg = nwarps + (int64_t)__shfl_sync(0xffffffffu, pend, 0);
-                    if (seg < nseg && lane == 0) pend = atomicAdd(a.tickets, 1u);
+                    armed = false;
+                    if (seg < nseg) arm(a, lane);
                 }
                 cur_seg = seg;
                 if (seg >= nseg) return 0;
@@ -874,7 +889,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
     w.gwarp = gwarp;
     w.nwarps = nwarps;
     w.static_claims = a.tickets == nullptr;
-    if (a.overlap && a.tickets) pass_gate(); // the slot's ticket word was last used by launch q-4
+    w.gate_ok = gate_open; // (variable-count overlap launches opened it together with the plan word)
     w.nb = FIXED ? a.count * a.var.row_bytes : 0;
     w.nreq = (FIXED && push) ? push_rbase[w.push_n] : a.nreq;
     if (FIXED) w.T = w.nb * w.nreq;
@@ -957,7 +972,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
         // issue up to S-1 groups ahead
         while (more && issued - consumed < (uint32_t)(S - 1)) {
             Piece pc;
-            const uint32_t total = w.template next_group<STAGE>(a, lane, pc);
+            const uint32_t total = w.template next_group<STAGE>(a, lane, pc, pass_gate);
             if (total == 0) {
                 more = false;
                 break;
@@ -997,6 +1012,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             if (lane == 0) a.dbg[blockIdx.x * 4 + 2] = globaltimer_ns();
         }
         pass_gate(); // overlap protocol: the loads above were harmless, the stores below are not
+        if (!w.static_claims && !w.gate_ok) { // ... and now the slot's ticket word is this launch's to use
+            w.gate_ok = true;
+            if (!w.armed) w.arm(a, lane);
+        }
         const int64_t my_dpos = desc[warp][st][lane].dpos;
         const uint32_t my_n = desc[warp][st][lane].n;
         const uint32_t my_pack = desc[warp][st][lane].pack;
@@ -1151,26 +1170,6 @@ struct PlanProto { // overlap protocol as the plan kernel sees it (all zero: ord
     unsigned int seq;
     int skip_wait, wait2_valid, wait4_valid;
 };
-
-// block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, *total = block sum
-template <int NT>
-__device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t *total) {
-    __shared__ int64_t warp_tot[NT / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int64_t inc = warp_incl_scan(v, lane);
-    if (lane == 31) warp_tot[wid] = inc;
-    __syncthreads();
-    int64_t base = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < NT / 32; k++) {
-        int64_t t = warp_tot[k];
-        if (k < wid) base += t;
-        tot += t;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + inc - v;
-}
 
 // The plan kernel: ONE pass. Every CTA takes a tile of PLAN_TILE requests (thread t: 4 consecutive ones), looks them up,
 // scans their sizes on chip, publishes the tile's byte count, resolves its offset by a decoupled look-back over the
@@ -1424,12 +1423,12 @@ __global__ void __launch_bounds__(256) dds_doorbell_kernel(const ddsk_var_t *__r
 
 // Test helper: hold `gridDim.x` SMs' worth of shared memory busy for `ns` nanoseconds (a stand-in for a training kernel
 // that shares the GPU with a prefetch queue; tests/test_gpu_parity.py uses it to attack the overlap protocol).
-__global__ void dds_occupy_kernel(unsigned long long ns) {
+__global__ void dds_occupy_kernel(unsigned long long ns, int smem_bytes) {
     extern __shared__ unsigned char occ_smem[];
-    occ_smem[threadIdx.x] = (unsigned char)threadIdx.x;
+    if ((int)threadIdx.x < smem_bytes) occ_smem[threadIdx.x] = (unsigned char)threadIdx.x;
     const uint64_t t0 = globaltimer_ns();
     while (globaltimer_ns() - t0 < ns) __nanosleep(1000);
-    if (occ_smem[threadIdx.x] == 255 && ns == 0) printf("");
+    if ((int)threadIdx.x < smem_bytes && occ_smem[threadIdx.x] == 255 && ns == 0) printf("");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1608,6 +1607,10 @@ void fill_overlap(GatherArgs &a, const ddsk_scratch_t *scr, int flags) {
     a.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
     a.seq = scr->ovl_seq;
     a.ovl = scr->ovl;
+    // segment tickets: the store's word for ordinary launches. Overlap launches: none for the fixed-count entry (plain
+    // striding -- measured: slot tickets cost 3 % on config 2, 1776 warps x 8 claims on one word per 85 us launch, and did
+    // not help a queue that shares the GPU either); the variable-count entries set the slot's own word below (their CTAs
+    // may start late, behind the plan kernel, and must not keep a fixed share of the work).
     a.tickets = a.overlap ? nullptr : scr->counters;
 }
 
@@ -1832,7 +1835,7 @@ int ddsk_doorbell_launch(const ddsk_var_t *vars_dev, ddsk_mailbox_t *mailbox_dev
 int ddsk_occupy(int ctas, int smem_bytes, unsigned long long ns, void *stream) {
     if (ctas <= 0) return 0;
     CUDA_TRY(cudaFuncSetAttribute(dds_occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    dds_occupy_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(ns);
+    dds_occupy_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(ns, smem_bytes);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

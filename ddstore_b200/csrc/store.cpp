@@ -1,15 +1,17 @@
 // ddstore_b200/csrc/store.cpp -- host side of the store: the reference's `class DDStore`
 // (/root/reference/include/ddstore.hpp:26-258, src/ddstore.cxx:19-96) re-built for B200:
-//   * a variable's shard is a cudaMalloc'd block of this rank's HBM (reference: MPI_Alloc_mem + memcpy,
+//   * a variable's shard is a CUDA VMM block of this rank's HBM (reference: MPI_Alloc_mem + memcpy,
 //     ddstore.hpp:44-49);
-//   * the "window" is the table of every rank's shard base mapped into this process through CUDA IPC
-//     (reference: MPI_Win_create, ddstore.hpp:56-61) -- NVSwitch makes every peer equally near;
+//   * the "window" is the table of every rank's shard base mapped into this process (VMM handle passed as a file
+//     descriptor; reference: MPI_Win_create, ddstore.hpp:56-61) -- NVSwitch makes every peer equally near;
 //   * lenlist / disp bookkeeping is the reference's (ddstore.hpp:75-89);
-//   * get() is a launch of the batched-gather kernel in kernels.cu (reference: MPI_Win_lock / MPI_Get /
-//     MPI_Win_unlock per sample, ddstore.hpp:222-237);
+//   * get() of a batch is a launch of the batched-gather kernel in kernels.cu (reference: MPI_Win_lock / MPI_Get /
+//     MPI_Win_unlock per sample, ddstore.hpp:222-237); a single get() is a mailbox round trip to a resident CTA;
 //   * epoch_begin/epoch_end are stream-sync + barrier with the reference's state machine
 //     (MPI_Win_fence, ddstore.cxx:51-77).
-// All CUDA work goes through the CUDA runtime C API and the ddsk_* launchers (kernels.h).
+// Also here: the bookkeeping of overlap runs (sequence numbers, scratch slots), the doorbell kernel's lifecycle, the
+// worker-thread pool of the pipelined host copies (ingest, pageable destinations), the windows of the collective
+// push fetch. All CUDA work goes through the CUDA runtime C API and the ddsk_* launchers (kernels.h).
 // There is no CPU data path: if no device is usable, dds_create fails with DDS_ERR_NO_DEVICE.
 #include <cuda_runtime_api.h>
 #include <sched.h>

@@ -247,6 +247,8 @@ class PrefetchLoader:
     def _issue(self, slot, idx):
         vals, labs, d_idx = self.bufs[slot]
         n = len(idx)
+        if n > vals.shape[0]:
+            raise ValueError(f"a fetch of {n} samples does not fit the loader's buffers ({vals.shape[0]} = batch_size x group)")
         keep = idx
         with torch.cuda.stream(self.stream):
             if torch.is_tensor(idx) and idx.is_cuda:

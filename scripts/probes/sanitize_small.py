@@ -49,5 +49,31 @@ ofx = [torch.zeros(500 * 2 * 28, dtype=torch.uint8, device="cuda") for _ in rang
 for k in range(6):
     store.get_batch("v7_uint8", fx, out=ofx[k & 1][:500 * 2 * 7], count=2, stream=side.cuda_stream, wait=False, overlap=True)
 store.wait()
+# round 2: large variable batch through the plan kernel (serialised and as an overlapped queue with scratch slots), the
+# single-request kernels (doorbell round trips, host and device destinations), the on-device verifier
+big = rng.integers(0, 2**32, size=(60000, 3), dtype=np.uint32).view(np.float32)
+store.add("big", big)
+st, ct = random_valid_requests(rng, [60000], 9000, max_count=12)
+exp, offs, _, _ = co.get_batch([big], st, ct)
+d_st, d_ct = torch.from_numpy(st).cuda(), torch.from_numpy(ct).cuda()
+ob = [torch.zeros(exp.size + 16, dtype=torch.uint8, device="cuda") for _ in range(2)]
+oo = [torch.zeros(9001, dtype=torch.int64, device="cuda") for _ in range(2)]
+assert store.get_batch("big", d_st, d_ct, out=ob[0], offsets=oo[0]) == exp.size
+assert ob[0][:exp.size].cpu().numpy().tobytes() == exp.tobytes() and oo[0].cpu().tolist() == offs.tolist()
+torch.cuda.synchronize()
+for k in range(7):
+    store.get_batch("big", d_st, d_ct, out=ob[k & 1], offsets=oo[k & 1], stream=side.cuda_stream, wait=False, overlap=True)
+assert store.wait() == exp.size
+for k in (0, 1):
+    assert ob[k][:exp.size].cpu().numpy().tobytes() == exp.tobytes() and oo[k].cpu().tolist() == offs.tolist()
+for start, cnt in ((0, 1), (17, 3), (59999, 1), (1234, 0)):
+    h = np.zeros((cnt, 3), np.float32); store.get("big", h, start); assert h.tobytes() == big[start:start + cnt].tobytes()
+    d = torch.zeros((cnt, 3), dtype=torch.float32, device="cuda"); store.get("big", d, start)
+    assert d.cpu().numpy().tobytes() == big[start:start + cnt].tobytes()
+store.init("syn", 5000, 8, 4); store.synth_fill("syn", 99)
+sid = torch.from_numpy(rng.integers(0, 5000, size=777)).cuda()
+osyn = torch.zeros(777 * 32, dtype=torch.uint8, device="cuda")
+store.get_batch("syn", sid, out=osyn, count=1)
+assert store.synth_verify("syn", osyn, sid, seed=99)[:2] == (0, 777)
 store.free(); store.close()
 print("sanitize-ok")

@@ -167,7 +167,9 @@ def test_prefetch_loader_matches_plain_loader():
         got2 = torch.cat([vals.clone() for vals, _ in PrefetchLoader(ds, dsamp, batch_size=48)]).cpu().numpy()
         assert got2.tobytes() == images[order].tobytes()
         # small batches grouped: 5 batches per launch, same batches out (host-side and device-resident samplers)
-        for samp in (sampler, dsamp):
+        dsamp16 = DeviceBatchSampler(len(ds), 16, rank=r, world_size=P, seed=1, device="cuda:0")
+        dsamp16.set_epoch(3)
+        for samp in (sampler, dsamp16):
             outs = [(v.clone(), l.clone()) for v, l in PrefetchLoader(ds, samp, batch_size=16, group=5)]
             assert [len(v) for v, _ in outs] == [16] * (len(order) // 16) + ([len(order) % 16] if len(order) % 16 else [])
             assert torch.cat([v for v, _ in outs]).cpu().numpy().tobytes() == images[order].tobytes()
