@@ -784,3 +784,39 @@ def test_single_request_kernel_alignments_and_errors(coracle):
         return True
 
     assert all(run_world(3, body))
+
+
+def test_large_pageable_destination_and_ingest(coracle):
+    """host copies that run through the worker-thread pool: a packed batch of tens of MB into a PAGEABLE ndarray (the
+    reference's np.zeros contract: copy engine -> pinned staging buffers -> worker threads), and dds_ingest of pageable
+    chunks into a pre-init'd shard (bounds and dtype checked like update)"""
+    torch = _torch()
+    rng = np.random.default_rng(21)
+    rows, disp = 120_000, 96  # 384 B rows, 46 MB shard
+    src = rng.integers(0, 2**32, size=(rows, disp), dtype=np.uint32).view(np.float32)
+
+    def body(store, r):
+        store.init("x", rows, disp, 4)
+        store.ingest("x", src[:70_001], 0)          # 26.9 MB: two staging buffers, ragged tail
+        store.ingest("x", src[70_001:], 70_001)
+        store.ingest_wait()
+        with pytest.raises(ValueError):
+            store.ingest("x", src[:10], rows - 5)   # outside the shard
+        with pytest.raises(ValueError, match="Invalid data type"):
+            store.ingest("x", src[:10].view(np.uint8).reshape(10, -1), 0)
+        ids = rng.integers(0, rows, size=90_000)    # 34.6 MB packed: the pipelined pageable path (>= 4 MB)
+        out = np.zeros((len(ids), disp), np.float32)
+        assert store.get_batch("x", ids, out=out, count=1) == out.nbytes
+        assert out.tobytes() == src[ids].tobytes()
+        pinned = torch.zeros((len(ids), disp), dtype=torch.float32).pin_memory().numpy()
+        store.get_batch("x", ids, out=pinned, count=1)
+        assert pinned.tobytes() == out.tobytes()
+        # an ingest right after a pageable fetch reuses the same staging buffers
+        store.ingest("x", src[:5000][::-1].copy(), 0)
+        store.ingest_wait()
+        chk = np.zeros((5000, disp), np.float32)
+        store.get_batch("x", np.arange(5000), out=chk, count=1)
+        assert chk.tobytes() == src[:5000][::-1].tobytes()
+        return True
+
+    assert all(run_world(1, body))
