@@ -355,17 +355,18 @@ struct GatherArgs {
     //   are on warps that are already running: no co-residency assumption, no deadlock.
     //   * a variable-count launch planned by the plan kernels owns scratch slot q & 3. griddepcontrol.wait waits for
     //     EVERY earlier grid of the stream (measured: with it, nothing of batch q moved before gather q-1 had finished),
-    //     so inside a run the two kernels of a batch are chained through memory instead: the plan kernel counts its
-    //     finished tiles and the last one publishes a plan-ready word (sequence number + packed total), the gather
-    //     spins on that word. The PLAN of batch q thus runs under the gather of batch q-1. The lookup kernel first checks that
+    //     so inside a run the two kernels of a batch are chained through memory instead: every tile of the plan kernel
+    //     adds (1 << 40 | its bytes) to the slot's plan word when its outputs are written, and the gather spins until
+    //     the word reads (tiles << 40 | packed total). The PLAN of batch q thus runs under the gather of batch q-1. The lookup kernel first checks that
     //     launch q-4, the slot's previous user, has retired. A kernel only ever spins on kernels launched before it.
     int overlap, skip_wait;
     int wait1_valid, wait2_valid; // q-1 / q-2 belong to the same run
     unsigned int seq;             // q (per-store counter of overlap launches, wraps)
     unsigned int *ovl;            // per slot (q & 3): [0..3] finished-warp counters, [4..7] done words, [8..11] segment
-                                  // tickets, [12..15] plan tiles done
+                                  // tickets
     int wait_plan;                // the plan kernels of this launch signal through plan_word[slot] (no grid dependency)
-    unsigned long long *plan_word; // [4] per slot: (sequence number & 0xFFFFFF) << 40 | packed total, published by the scan kernel
+    unsigned long long *plan_word; // [4] per slot: (finished plan tiles << 40) | packed total so far (see dds_plan_kernel)
+    int64_t plan_tiles;            // tiles of this launch's plan
     unsigned int *tickets;        // the segment ticket word of this launch (counters[0], or ovl[8 + slot]); NULL: static striding
     unsigned long long *host_mirror; // zero-copy pinned host words: [0] status, [1] packed total (written at kernel end)
     unsigned long long *dbg;         // DDS_DEBUG_TIMING: per CTA [entry, plan done, first data, last warp done] (globaltimer ns)
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
                     bool ok = true;
                     if (lane == 0) {
                         pw = ld_acquire_u64(&a.plan_word[a.seq & 3u]);
-                        ok = (pw >> 40) == (unsigned long long)(a.seq & 0xFFFFFFu);
+                        ok = (pw >> 40) == (unsigned long long)a.plan_tiles; // every tile of the plan has added its share
                     } else if (lane == 1 && need_gate) {
                         ok = (int)(ld_acquire_u32(&a.ovl[4 + ((a.seq - 2u) & 3u)]) - (a.seq - 2u)) >= 0;
                     }
@@ -1072,6 +1073,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dds_gather_kernel(const __grid_con
             if (done == (unsigned int)(nwarps - 1)) {
                 a.ovl[slot] = 0;
                 a.ovl[8 + slot] = 0;
+                if (a.wait_plan) a.plan_word[slot] = 0; // (every CTA has read the total long ago)
                 if (a.wait1_valid) spin_until_done(a.ovl, a.seq - 1u, a.status, a.nreq);
                 __threadfence();
                 st_release_u32(&a.ovl[4 + slot], a.seq);
@@ -1166,7 +1168,6 @@ struct PlanProto { // overlap protocol as the plan kernel sees it (all zero: ord
     unsigned long long *dbg; // DDS_DEBUG_TIMING
     unsigned int *ovl;
     unsigned long long *plan_word;
-    int64_t *plan_total; // [4] per slot: the last tile parks the packed total here for whichever tile finishes last
     unsigned int seq;
     int skip_wait, wait2_valid, wait4_valid;
 };
@@ -1276,21 +1277,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) dds_plan_kernel(const __grid_con
         if (offsets_out) offsets_out[nreq] = T;
     }
     if (pr.dbg && threadIdx.x == 0) atomicMax(&pr.dbg[4096 + 1], (unsigned long long)globaltimer_ns());
-    if (pr.ovl) { // overlap run: the gather of this batch spins on the plan word instead of waiting for the grid. The
-                  // last tile to finish re-arms the count and publishes "ready" + the packed total.
+    if (pr.ovl) {
+        // overlap run: the gather of this batch spins on the slot's plan word instead of waiting for the grid. Every tile
+        // adds (1 << 40 | its bytes) with ONE fire-and-forget release-add once its outputs are written (the barrier makes
+        // the other threads' stores part of what thread 0 releases): the word reads (tiles << 40 | packed total) exactly
+        // when the plan is complete. The gather's retiring warp clears it for the slot's next user.
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int slot = pr.seq & 3u;
-            if (last_tile) *(volatile int64_t *)&pr.plan_total[slot] = T;
-            __threadfence();
-            if (atomicAdd(&pr.ovl[12 + slot], 1u) == gridDim.x - 1) {
-                pr.ovl[12 + slot] = 0;
-                __threadfence();
-                const unsigned long long Tw = (unsigned long long)*(volatile int64_t *)&pr.plan_total[slot];
-                __threadfence();
-                st_release_u64(&pr.plan_word[slot], ((unsigned long long)(pr.seq & 0xFFFFFFu) << 40) | (Tw & 0xFFFFFFFFFFull));
-            }
-        }
+        if (threadIdx.x == 0)
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&pr.plan_word[pr.seq & 3u]),
+                         "l"((1ull << 40) | ((unsigned long long)agg & 0xFFFFFFFFFFull))
+                         : "memory");
     }
 }
 
@@ -1725,7 +1721,6 @@ static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq
         pr.dbg = g_dbg ? g_dbg + (size_t)(scr->ovl_seq & 1u) * kDbgRegion : nullptr;
         pr.ovl = scr->ovl;
         pr.plan_word = scr->plan_word;
-        pr.plan_total = (int64_t *)(scr->plan_word + 4);
         pr.seq = scr->ovl_seq;
         pr.skip_wait = (flags & DDSK_F_SKIP_WAIT) ? 1 : 0;
         pr.wait2_valid = (flags & DDSK_F_PREV2) ? 1 : 0;
@@ -1749,6 +1744,7 @@ static int plan_and_gather(const ddsk_var_t *var, const PlanSrc &p, int64_t nreq
         a.tickets = scr->ovl + 8 + (a.seq & 3u);
         a.wait_plan = 1; // (a.skip_wait: inside a run the gather skips the grid wait and spins on the plan-ready word)
         a.plan_word = scr->plan_word;
+        a.plan_tiles = tiles;
     }
     return launch_gather<false>(a, st);
 }
