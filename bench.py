@@ -518,7 +518,7 @@ def run_configs(ctx, args, names, ref):
     import torch
     from ddstore_b200 import PyDDStore
     N, rank, dev, st = ctx.N, ctx.rank, ctx.dev, ctx.stream
-    K, W, R = max(5, min(args.steps, 10)), 3, max(3, min(args.repeats, 5))
+    K, W, R = max(5, min(args.steps, 20)), 3, max(3, min(args.repeats, 5))
     sc = args.config_scale
     rng = np.random.default_rng(1234 + rank)
     entries = []
@@ -549,26 +549,29 @@ def run_configs(ctx, args, names, ref):
         d_start, d_len = torch.from_numpy(sstart[:-1].copy()).to(dev), torch.from_numpy(L).to(dev)
         store.set_sample_index("x", d_start, d_len)
         for B in (4096, 16384):
-            ids = torch.from_numpy(rng.integers(0, nsamp, size=B)).to(dev)
-            s_, c_ = d_start[ids].contiguous(), d_len[ids].contiguous()
-            rows = int(c_.sum().item())
-            nbytes = rows * 4
-            outs = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            # FOUR different id sets, rotated step by step (a loader never asks for the same samples twice in a row)
+            NS = 4
+            ids = [torch.from_numpy(rng.integers(0, nsamp, size=B)).to(dev) for _ in range(NS)]
+            s_ = [d_start[i].contiguous() for i in ids]
+            c_ = [d_len[i].contiguous() for i in ids]
+            rows = [int(c.sum().item()) for c in c_]
+            nbytes = float(np.mean(rows)) * 4
+            outs = [torch.empty(max(rows) * 4, dtype=torch.uint8, device=dev) for _ in range(2)]
             offs = [torch.empty(B + 1, dtype=torch.int64, device=dev) for _ in range(2)]
             wl = f"configs[2]: variable-length 100..10000 float32 samples, {nsamp} samples ({int(sstart[-1]) * 4 / 1e9:.1f} GB) over {N} GPU(s), B={B} per GPU"
-            for mode, fn in (("", lambda i: store.get_batch("x", s_, c_, out=outs[i & 1], offsets=offs[i & 1], stream=st,
+            for mode, fn in (("", lambda i: store.get_batch("x", s_[i % NS], c_[i % NS], out=outs[i & 1], offsets=offs[i & 1], stream=st,
                                                            wait=False, overlap=True)),
-                             ("_by_sample_id", lambda i: store.get_samples("x", ids, outs[i & 1], offsets=offs[i & 1],
+                             ("_by_sample_id", lambda i: store.get_samples("x", ids[i % NS], outs[i & 1], offsets=offs[i & 1],
                                                                           stream=st, wait=False, overlap=True))):
                 ms = ctx.timed_blocks(store, fn, K, W, R)
-                last = (W + R * K - 1) & 1
-                ver = verify_entry(ctx, store, "x", outs[last], s_, c_, 1, offs[last], SEED, rows)
+                li = W + R * K - 1  # the last step: which ids, which buffer
+                ver = verify_entry(ctx, store, "x", outs[li & 1], s_[li % NS], c_[li % NS], 1, offs[li & 1], SEED, rows[li % NS])
                 # the same queue with every launch waiting for the previous one (no DDS_OVERLAP)
-                ser = ctx.timed_blocks(store, (lambda i, m=mode: store.get_batch("x", s_, c_, out=outs[0], offsets=offs[0], stream=st, wait=False)
-                                               if not m else store.get_samples("x", ids, outs[0], offsets=offs[0], stream=st, wait=False)),
+                ser = ctx.timed_blocks(store, (lambda i, m=mode: store.get_batch("x", s_[i % NS], c_[i % NS], out=outs[0], offsets=offs[0], stream=st, wait=False)
+                                               if not m else store.get_samples("x", ids[i % NS], outs[0], offsets=offs[0], stream=st, wait=False)),
                                        K, W, 3)
                 entry(f"cfg3{mode}_B{B}", wl + (", explicit (start, count) arrays" if not mode else ", by sample id (device-resident index)"),
-                      ms, nbytes, B, ver, {"serialized_ms_per_step": float(np.median(ser)), "queue": "DDS_OVERLAP double-buffered"})
+                      ms, nbytes, B, ver, {"serialized_ms_per_step": float(np.median(ser)), "queue": "DDS_OVERLAP double-buffered, 4 id sets rotated"})
         store.free()
         store.close()
 

@@ -162,6 +162,9 @@ int ddsk_synth_verify(const ddsk_var_t *var, const void *packed_dev, const int64
                       const int64_t *counts_dev_or_null, int64_t fixed_count, const int64_t *offsets_dev_or_null,
                       int64_t nreq, int64_t disp, int itemsize, uint64_t seed, unsigned long long *out_dev, void *stream);
 
+/* pull [base, base + bytes) into the persisting part of L2 (no-op with DDS_L2_PERSIST=0) */
+int ddsk_l2_warm(const void *base_dev, size_t bytes, void *stream);
+
 /* test helper: `ctas` CTAs holding `smem_bytes` of shared memory each for `ns` nanoseconds on `stream` */
 int ddsk_occupy(int ctas, int smem_bytes, unsigned long long ns, void *stream);
 

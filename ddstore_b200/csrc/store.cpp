@@ -1343,6 +1343,21 @@ int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_st
     CU(cudaStreamSynchronize(s->stream));
     if (!tables_on_device) v->h_tab_count.assign(row_count, row_count + nsamples); // sizes a host destination needs
     v->nsamples = nsamples;
+    // room in the persisting part of L2 for the tables (the plan kernel asks for it with an access-policy window): the
+    // gather streams hundreds of MB per batch through L2 and would otherwise evict them between batches
+    {
+        size_t want = 0;
+        for (auto &x : s->vars) want += (size_t)x.second.nsamples * 16;
+        int maxp = 0;
+        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, s->device) == cudaSuccess && maxp > 0)
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, (size_t)maxp));
+        (void)cudaGetLastError();
+        if (maxp > 0 && (size_t)nsamples * 16 <= (size_t)maxp) { // warm it now: every later lookup hits L2
+            (void)ddsk_l2_warm(v->d_tab, (size_t)nsamples * 16, s->stream);
+            (void)cudaStreamSynchronize(s->stream);
+            (void)cudaGetLastError();
+        }
+    }
     return DDS_OK;
 }
 
