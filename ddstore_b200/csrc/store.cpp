@@ -1349,8 +1349,10 @@ int dds_set_sample_index(dds_store_t *s, const char *name, const int64_t *row_st
         size_t want = 0;
         for (auto &x : s->vars) want += (size_t)x.second.nsamples * 16;
         int maxp = 0;
-        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, s->device) == cudaSuccess && maxp > 0)
-            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, (size_t)maxp));
+        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, s->device) != cudaSuccess) maxp = 0;
+        // (at most 32 MiB -- a quarter of the B200's L2 -- is set aside: the rest of the process shares this cache)
+        maxp = (int)std::min<size_t>((size_t)std::max(maxp, 0), (size_t)32 << 20);
+        if (maxp > 0) (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, (size_t)maxp));
         (void)cudaGetLastError();
         if (maxp > 0 && (size_t)nsamples * 16 <= (size_t)maxp) { // warm it now: every later lookup hits L2
             (void)ddsk_l2_warm(v->d_tab, (size_t)nsamples * 16, s->stream);
