@@ -456,7 +456,9 @@ def test_plan_variants_agree(tmp_path, mode):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "plan_variant.py"
     script.write_text(PLAN_SCRIPT.format(root=root))
-    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_SMEM_PLAN=mode), capture_output=True,
+    # (mode 1 also raises the shared-memory plan's limit to its maximum, so both of its kernel variants -- 4096 and 8192
+    # requests -- are exercised; by default only batches of <= 1024 requests plan in shared memory)
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, DDS_SMEM_PLAN=mode, DDS_SMEM_PLAN_MAX="8192"), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "plan-ok" in r.stdout, r.stdout + r.stderr
 
