@@ -310,6 +310,78 @@ class PrefetchLoader:
             b0 += n
 
 
+class RaggedPrefetchLoader:
+    """Double-buffered prefetch for a RaggedDataset (variable-length, multi-array samples): while the consumer works on
+    batch k, batch k+1 -- every variable of it, ONE launch (`dds_get_samples_multi`) -- is planned and gathered on a side
+    stream into the other buffer set. Consecutive fetches are queued with overlap=True, so the plan of batch k+1 runs
+    under the gather of batch k (the kernel enforces that batch k+2 writes nothing before batch k has retired).
+
+    sampler: iterable of sample ids on the host (e.g. DistributedSampler): the packed sizes come from the host copy of
+    the row counts. Yields {name: (packed rows tensor [sum(count), ...width], int64 row offsets [B+1])}; a batch stays
+    valid until the next-but-one fetch."""
+
+    def __init__(self, dataset, sampler, batch_size, drop_last=False, depth=2):
+        if len(dataset.names) > 4:
+            raise ValueError("RaggedPrefetchLoader fetches all variables in one launch (<= 4 variables)")
+        self.ds, self.sampler, self.bs, self.drop_last, self.depth = dataset, sampler, batch_size, drop_last, max(2, depth)
+        dev = dataset.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in range(self.depth)]
+        self.bufs = [None] * self.depth   # per slot: {name: uint8 buffer}, grown on demand
+        self.offs = [[torch.empty(batch_size + 1, dtype=torch.int64, device=dev) for _ in dataset.names] for _ in range(self.depth)]
+        self.d_ids = [torch.empty(batch_size, dtype=torch.int64, device=dev) for _ in range(self.depth)]
+
+    def _batches(self):
+        cur = []
+        for i in self.sampler:
+            cur.append(int(i))
+            if len(cur) == self.bs:
+                yield cur
+                cur = []
+        if cur and not self.drop_last:
+            yield cur
+
+    def _issue(self, slot, idx):
+        ds = self.ds
+        ids = np.asarray(idx, dtype=np.int64)
+        rows = [int(ds.counts[name][ids].sum()) for name in ds.names]  # host-side sizes only
+        need = [max(r, 1) * ds.row_bytes[name] for r, name in zip(rows, ds.names)]
+        if self.bufs[slot] is None or any(b.numel() < n for b, n in zip(self.bufs[slot], need)):
+            # (grown rarely; a fresh buffer cannot still be in use by an earlier fetch)
+            self.bufs[slot] = [torch.empty(int(n * 1.25) + 64, dtype=torch.uint8, device=ds.device) for n in need]
+        keep = torch.from_numpy(ids).pin_memory()
+        n = len(ids)
+        with torch.cuda.stream(self.stream):
+            self.d_ids[slot][:n].copy_(keep, non_blocking=True)
+            ds.ddstore.get_samples_multi(ds.names, self.d_ids[slot][:n], self.bufs[slot], offsets=[o[:n + 1] for o in self.offs[slot]],
+                                         stream=self.stream.cuda_stream, wait=False, overlap=True)
+            self.events[slot].record(self.stream)
+        return n, rows, keep
+
+    def __iter__(self):
+        consumer = torch.cuda.current_stream(self.ds.device)
+        pending, slot = [], 0
+        for idx in self._batches():
+            self.stream.wait_stream(consumer)  # the slot's previous tenant has been consumed by whatever is queued so far
+            pending.append((slot,) + self._issue(slot, idx))
+            slot = (slot + 1) % self.depth
+            if len(pending) == self.depth:
+                yield self._take(pending.pop(0), consumer)
+        while pending:
+            yield self._take(pending.pop(0), consumer)
+        self.ds.ddstore.wait()  # surface any fetch error of the epoch
+
+    def _take(self, item, consumer):
+        slot, n, rows, _ = item
+        consumer.wait_event(self.events[slot])
+        ds, out = self.ds, {}
+        for k, name in enumerate(ds.names):
+            nb = rows[k] * ds.row_bytes[name]
+            buf = self.bufs[slot][k][:nb].view(ds.dtypes[name]).view((rows[k],) + tuple(ds.widths[name]))
+            out[name] = (buf, self.offs[slot][k][:n + 1] // ds.row_bytes[name])
+        return out
+
+
 def ingest_chunks(store, name, chunks, first_row=0):
     """Streaming ingest: fill a pre-`init`'d shard from an iterator of host arrays (the
     reference's init + update-in-chunks pattern, include/ddstore.hpp:110-195). Every chunk goes through the library's

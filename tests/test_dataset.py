@@ -130,6 +130,27 @@ def test_ragged_dataset_config4_shape():
             sf, se = sample(i)
             assert f[fo[k]:fo[k + 1]].cpu().numpy().tobytes() == sf.tobytes()
             assert ed[eo[k]:eo[k + 1]].cpu().numpy().tobytes() == se.tobytes()
+        # the same dataset through the double-buffered prefetch loader (overlapped multi-array fetches on a side stream,
+        # with consumer work queued between the batches), a whole shuffled epoch, ragged last batch included
+        from ddstore_b200.dataset import RaggedPrefetchLoader
+        from torch.utils.data.distributed import DistributedSampler
+        sampler = DistributedSampler(ds, num_replicas=P, rank=r, shuffle=True, seed=3)
+        sampler.set_epoch(1)
+        order = list(iter(sampler))
+        seen, acc = 0, torch.zeros((), device="cuda:0")
+        for batch in RaggedPrefetchLoader(ds, sampler, batch_size=64):
+            f, fo = batch["node_feat"]
+            ed, eo = batch["edge_index"]
+            acc = acc + torch.nan_to_num(f).abs().sum() + ed.sum()   # consumer work on the current stream
+            fo, eo = fo.cpu().numpy(), eo.cpu().numpy()
+            nb = len(fo) - 1
+            for k in range(0, nb, 7):
+                sf, se = sample(order[seen + k])
+                assert f[fo[k]:fo[k + 1]].cpu().numpy().tobytes() == sf.tobytes()
+                assert ed[eo[k]:eo[k + 1]].cpu().numpy().tobytes() == se.tobytes()
+            assert fo[-1] == f.shape[0] and eo[-1] == ed.shape[0]
+            seen += nb
+        assert seen == len(order)
         ds.free()
         return True
 

@@ -822,3 +822,45 @@ def test_large_pageable_destination_and_ingest(coracle):
         return True
 
     assert all(run_world(1, body))
+
+
+def test_doorbell_kernel_lifecycle():
+    """the resident CTA behind get(): it leaves by itself when idle and a later get() starts a fresh one without losing
+    or repeating a request; a device-wide synchronize, an async batch and a free() in between all work; DDS_DOORBELL=0
+    semantics (1-CTA launch per call) are covered by the plan-variant subprocess tests' get() calls"""
+    import time
+    torch = _torch()
+    rng = np.random.default_rng(9)
+    shard = rng.integers(0, 2**32, size=(5000, 33), dtype=np.uint32).view(np.float32)
+
+    def body(store, r):
+        store.add("x", shard)
+        store.add("b", shard.view(np.uint8).reshape(5000, -1)[:, :7].copy())
+        out = np.zeros((1, 33), np.float32)
+        dout = torch.zeros((2, 33), dtype=torch.float32, device="cuda")
+        for k in range(300):
+            i = int(rng.integers(0, 4998))
+            if k % 3 == 0:
+                store.get("x", dout, i)
+                assert dout.cpu().numpy().tobytes() == shard[i:i + 2].tobytes()
+            else:
+                store.get("x", out, i)
+                assert out.tobytes() == shard[i:i + 1].tobytes()
+            if k % 50 == 10:
+                time.sleep(0.003)            # longer than the idle timeout: the kernel has left, the next get restarts it
+            if k % 50 == 20:
+                torch.cuda.synchronize()     # must not hang on the resident kernel
+            if k % 50 == 30:                 # an async batch in between (the store parks the doorbell when it must sync)
+                ids = torch.from_numpy(rng.integers(0, 5000, size=64)).cuda()
+                big = torch.zeros((64, 33), dtype=torch.float32, device="cuda")
+                store.get_batch("x", ids, out=big, count=1, wait=False)
+                assert store.wait() == big.numel() * 4 and big.cpu().numpy().tobytes() == shard[ids.cpu().numpy()].tobytes()
+            if k % 50 == 40:
+                with pytest.raises(ValueError, match="Invalid count on target"):
+                    store.get("x", np.zeros((3, 33), np.float32), 4998)
+        b = np.zeros((4, 7), np.uint8)
+        store.get("b", b, 100)               # another variable, byte-granular rows
+        assert b.tobytes() == shard.view(np.uint8).reshape(5000, -1)[100:104, :7].tobytes()
+        return True
+
+    assert all(run_world(1, body))
