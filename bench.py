@@ -965,7 +965,13 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "gather_fixed_traffic.json" if N == 1 else "r2_nvlink_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"] if N == 1 else tj.get("nvlink_rx_bytes_per_launch")
+        if N == 1:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        else:
+            # NVLink bytes INTO this GPU per launch: measured at N=2 with ncu on rank 0 (payload x 1.125 response bytes +
+            # the peers' read requests, 0.1875 per payload byte served), scaled to this N's remote fraction
+            r = tj.get("per_payload_byte", {"response_header": 0.125, "read_request_packet": 0.1875})
+            traffic = step_bytes * (N - 1) / N * (1.0 + r["response_header"] + r["read_request_packet"])
     roofline.update({"traffic": traffic, "kernel": "dds_gather_kernel<FIXED,12,4,4096>", "per_launch_ms": ms_step,
                      "per_launch_event_pair_ms": pair_ms, "per_launch_event_pair_ms_p10_p50_p90": pair_pcts,
                      "note": "per_launch_ms = median K-step block / K with the launches overlapping head-to-tail (DDS_OVERLAP); "
