@@ -10,7 +10,8 @@
 //
 // Kernel design (bandwidth-bound byte mover, no tensor cores):
 //   * The packed destination byte range [0, T) is cut into segments that warps claim dynamically
-//     (one atomic per segment; statically strided for DDS_OVERLAP launches), so load balance is by
+//     (one atomic per segment, requested one segment ahead; fixed-count DDS_OVERLAP launches stride
+//     statically), so load balance is by
 //     BYTES, not by request count (lengths differ 100x in the variable-length configs) and not by
 //     owner (remote rows are slower than local).
 //   * Every warp is an autonomous pipeline with a private ring of S shared-memory stages. A stage
@@ -26,15 +27,24 @@
 //       - different phase -> all lanes read two aligned 16-byte vectors from shared memory,
 //         funnel-shift (or word-select) them into place and issue aligned 128-bit stores.
 //   * Request offsets in the packed buffer are an exclusive prefix sum of request sizes: arithmetic
-//     in the fixed-count entry. For variable counts and <= 8192 requests EVERY CTA computes the whole
-//     plan (lookup + checks + scan) redundantly into its own shared memory -- no inter-CTA
-//     dependency at all, and the walk's searches / descriptor loads are shared-memory reads.
-//     Larger batches are planned by two small kernels into global scratch, which also fill a
-//     segment table (request covering every 16 KiB boundary) so a segment claim is one load.
-//     The (start, count) of a request may come from a device-resident per-sample index (sample ids in).
+//     in the fixed-count entry. For variable counts the PLAN (lookup + checks + scan) is
+//       - one single-pass kernel (dds_plan_kernel: decoupled look-back over 1024-request tiles), which
+//         also fills a segment table (request covering every 16 KiB boundary) so that a segment claim
+//         of the gather is one load; in an overlapped queue it runs UNDER the previous batch's gather,
+//         in a scratch slot of its own, chained to its gather through a memory word instead of the grid
+//         dependency; or
+//       - for small batches, computed by EVERY CTA redundantly into its own shared memory (no
+//         inter-CTA dependency, one launch per batch).
+//     The (start, count) of a request may come from a device-resident per-sample index (sample ids in;
+//     the table is kept in the persisting part of L2).
 //   * Launches carry the programmatic-dependent-launch attribute; independent batches
 //     (DDS_OVERLAP) skip the grid wait and overlap head-to-tail, under a contract the kernel
-//     enforces itself with per-launch generation words (see the overlap protocol below).
+//     enforces itself with per-launch generation words (see the overlap protocol at GatherArgs).
+//
+// Also here: the single-request kernels of the legacy one-get()-per-sample loop (dds_doorbell_kernel: a
+// resident CTA polling a mailbox in pinned memory, no launch per call; dds_small_get_kernel), the
+// collective owner-push variant of the fetch (the push section of dds_gather_kernel), and the
+// bench / test helpers (payload generator, on-device verifier, SM occupier).
 //
 // Nothing here calls a library kernel; everything is launched from the ddsk_* functions at the end.
 #include <cuda_runtime.h>
