@@ -172,6 +172,17 @@ def cfg4_tables(nsamp):
     return np.concatenate([[0], np.cumsum(n)]), n, np.concatenate([[0], np.cumsum(e)]), e
 
 
+def workload_config(N, total, B):
+    """the `config` object BOTH arms print: it names the workload (BASELINE.json configs[1]); how an arm runs it -- the
+    GPU arm's queue and kernel geometry, the CPU arm's bounded sample -- is said elsewhere in its line"""
+    per = total // N
+    return {"workload": "configs[1]: 10M fixed-length 1024-float32 samples, uniform-random batch fetch",
+            "total_samples": total, "row_bytes": ROW_BYTES, "batch_per_gpu": B, "bytes_per_step_per_gpu": B * ROW_BYTES,
+            "store_bytes": total * ROW_BYTES,
+            "l2": "inputs larger than L2 (random rows of a %.1f GB shard per GPU; 268 MB output)" % (per * ROW_BYTES / 1e9),
+            "parallelism": f"store sharded over {N} GPU(s) by contiguous blocks of rows (the reference's lenlist partition), no collective"}
+
+
 # --------------------------------------------------------------------------------------------- reference arm
 def host_cpu_info():
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -399,8 +410,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: fixed-length 1024-float32 samples, uniform-random batch fetch "
-                                   "(bounded CPU sample of the 10M-sample store)", "row_bytes": ROW_BYTES},
+            "config": workload_config(args.gpus, args.samples, args.batch),
             "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "host_cpus": info["host_cpus"], "cpu_set": info["cpu_set"],
             "samples_per_s": info["samples_per_s"],
@@ -1011,15 +1021,11 @@ def run_ours(args):
                 "serialized_ms_per_step": float(np.median(ser_blocks)),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "configs[1]: 10M fixed-length 1024-float32 samples, uniform-random batch fetch",
-                           "total_samples": total, "row_bytes": ROW_BYTES, "batch_per_gpu": B,
-                           "bytes_per_step_per_gpu": step_bytes, "store_bytes": total * ROW_BYTES,
-                           "l2": "inputs larger than L2 (random rows of a %.1f GB shard per GPU; 268 MB output)"
-                                 % (nrows * ROW_BYTES / 1e9),
-                           "parallelism": f"store sharded over {N} GPU(s), VMM peer mappings, no collective",
-                           "queue": "K independent batches per block queued asynchronously on one stream with DDS_OVERLAP into "
+                "config": workload_config(N, total, B),
+                "method": {"queue": "K independent batches per block queued asynchronously on one stream with DDS_OVERLAP into "
                                     "two alternating output buffers (double-buffered prefetch; the kernel enforces that batch "
                                     "k+2 writes nothing before batch k retired); R blocks, median reported",
+                           "mapping": "VMM peer mappings (fd passing), no NCCL in the data path",
                            "gather_geometry": {"ctas": geom[0].value, "warps_per_cta": geom[1].value,
                                                "stages": geom[2].value, "chunk_bytes": geom[3].value,
                                                "smem_bytes": geom[4].value}},

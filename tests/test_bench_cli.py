@@ -20,6 +20,12 @@ def test_reference_arm_json_contract():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # both arms print the SAME workload description (the driver compares them); the bounded sample is said in cpu_baseline
+    import bench
+    assert d["config"] == bench.workload_config(1, bench.TOTAL_SAMPLES, 65536)
+    assert d["host_cpus"] >= 1 and "cpu_set" in d
+    names = {c["name"] for c in d["configs"]}
+    assert {"cfg3_B4096", "cfg3_B16384", "cfg4_B4096", "cfg5_R4096", "per_sample_loop"} <= names
 
 
 def test_reference_arm_other_ranks_exit_quietly():
