@@ -67,7 +67,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only")
-    ap.add_argument("--no-push", action="store_true", help="N > 1: skip the collective owner-push variant")
+    ap.add_argument("--push", action="store_true",
+                    help="N > 1: also measure the collective owner-push fetch (slower than the pull at every N measured, "
+                         "profiles/r2_configs.md; a rank that dies inside it makes the others trap after 30 s, so it is not part "
+                         "of the default run)")
     ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg1,persample,ingest,prefetch")
     ap.add_argument("--config-scale", type=float, default=1.0, help="shrink the stores of the extra configs (tests)")
     return ap.parse_args()
@@ -909,7 +912,7 @@ def run_ours(args):
     # ---- N > 1: the same steps as a COLLECTIVE owner-push fetch (every rank fetches in every step anyway): posted NVLink
     # writes instead of pull reads. Same rows, same packed layout, in the rank's window of the store.
     push = None
-    if N > 1 and not args.no_push:
+    if N > 1 and args.push:
         store.push_setup(B, step_bytes)
         last_view = [None, None]
 

@@ -6,7 +6,7 @@ NG=$(nvidia-smi -L | wc -l)
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -v 2>&1 | tail -25 | tee gpurun_out/r2_gpu_multi_tests_n$NG.txt
 for N in $NG 4; do
   [ "$N" -gt "$NG" ] && continue
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N bench.py --gpus $N --steps 20 --warmup 5 --push > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
   tail -2 gpurun_out/r2_bench_n$N.err
   python - $N <<'PY'
 import json,sys
