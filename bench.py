@@ -364,8 +364,8 @@ def cpu_reference_configs(names, nthreads, steps=3, warmup=1):
         sizes = list(CFG5_SIZES) if "cfg5" in names else []
         for R in sizes + ([512] if "cfg1" in names else []):
             rows_per = max(64, (32 << 20) // R)  # >= 32 MiB (or 64 rows) per rank-thread
-            if R * rows_per * P > (24 << 30):
-                rows_per = max(4, (24 << 30) // (R * P))
+            if R * rows_per * P > (8 << 30):  # bound the host memory (twice this: add() copies) and the set-up time
+                rows_per = max(4, (8 << 30) // (R * P))
             shards = [co.synth_rows(SEED, r * rows_per, rows_per, R // 4, np.float32) for r in range(P)]
             w = O.RefWorld(P)
             w.add("s", shards)
