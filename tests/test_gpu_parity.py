@@ -864,3 +864,79 @@ def test_doorbell_kernel_lifecycle():
         return True
 
     assert all(run_world(1, body))
+
+
+def test_overlapped_variable_queue_edge_cases(coracle):
+    """the memory-chained plan/gather protocol on the awkward batches of an overlapped run: all-zero counts (nothing to
+    walk), a single request, a batch that does not fit its buffer (capacity error, nothing written), a bad sample id,
+    more requests than the scratch slots hold (they grow mid-run) -- each followed by ordinary batches that must be
+    delivered intact, with the error reported by wait() as the first of the queue"""
+    torch = _torch()
+    rng = np.random.default_rng(2718)
+    nsamp = 20_000
+    L = rng.integers(0, 60, size=nsamp)
+    sstart = np.concatenate([[0], np.cumsum(L)])
+    shard = rng.integers(0, 2**32, size=(int(sstart[-1]), 5), dtype=np.uint32).view(np.float32)  # 20 B rows
+
+    def body(store, r):
+        store.add("x", shard)
+        store.set_sample_index("x", sstart[:-1], L)
+        dev = torch.device("cuda", 0)
+        side = torch.cuda.Stream(device=dev)
+        st = side.cuda_stream
+        good = [rng.integers(0, nsamp, size=n) for n in (9000, 12000, 9500, 30000, 9000, 9100)]
+        exps = [coracle.get_batch([shard], sstart[g], L[g]) for g in good]
+        cap = max(e[0].size for e in exps) + 64
+        bufs = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        offs = [torch.zeros(30001, dtype=torch.int64, device=dev) for _ in range(2)]
+        d_good = [torch.from_numpy(g).to(dev) for g in good]
+        torch.cuda.synchronize()
+
+        def check(slot, k):
+            e, eo, bad, _ = exps[k]
+            assert bad == -1 and bufs[slot][:e.size].cpu().numpy().tobytes() == e.tobytes(), (slot, k)
+            assert offs[slot][:len(good[k]) + 1].cpu().tolist() == eo.tolist()
+
+        def q(ids, slot, n=None):
+            n = len(ids) if n is None else n
+            store.get_samples("x", ids, bufs[slot], offsets=offs[slot][:n + 1], stream=st, wait=False, overlap=True)
+
+        # 1. zero-length batch (explicit counts all 0) and a single request inside a run
+        zeros = torch.zeros(9000, dtype=torch.int64, device=dev)
+        q(d_good[0], 0)
+        store.get_batch("x", d_good[0].clamp(max=100), zeros, out=bufs[1], offsets=offs[1][:9001], stream=st, wait=False, overlap=True)
+        q(d_good[1], 0)
+        one = torch.tensor([int(good[2][0])], device=dev)
+        q(one, 1)
+        q(d_good[2], 0)
+        assert store.wait() == exps[2][0].size
+        check(0, 2)
+        e1 = coracle.get_batch([shard], sstart[good[2][:1]], L[good[2][:1]])[0]
+        assert bufs[1][:e1.size].cpu().numpy().tobytes() == e1.tobytes() and offs[1][:2].cpu().tolist() == [0, e1.size]
+        # 2. the scratch slots grow in the middle of a run (30000 requests after 9000-12000), results stay right
+        q(d_good[0], 0); q(d_good[1], 1); q(d_good[3], 0); q(d_good[4], 1); q(d_good[5], 0)
+        assert store.wait() == exps[5][0].size
+        check(0, 5); check(1, 4)
+        # 3. a batch that does not fit (capacity) in the middle: reported, its buffer untouched, neighbours intact
+        small = torch.full((4096,), 7, dtype=torch.uint8, device=dev)
+        q(d_good[0], 0)
+        store.get_samples("x", d_good[1], small, stream=st, wait=False, overlap=True)
+        q(d_good[2], 1)
+        with pytest.raises(ValueError, match="too small"):
+            store.wait()
+        assert int(small.min()) == 7 and int(small.max()) == 7
+        check(0, 0); check(1, 2)
+        # 4. a bad sample id in the middle: first error of the queue, with its index; the run after it works
+        bad = d_good[4].clone()
+        bad[4321] = nsamp + 5
+        q(d_good[0], 0); q(bad, 1); q(d_good[2], 0)
+        with pytest.raises(ValueError, match="sample id"):
+            store.wait()
+        assert store.last_bad_index == 4321
+        check(0, 2)
+        q(d_good[4], 1); q(d_good[5], 0)
+        assert store.wait() == exps[5][0].size
+        check(1, 4); check(0, 5)
+        return True
+
+    assert all(run_world(1, body))
