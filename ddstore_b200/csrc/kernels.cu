@@ -383,10 +383,8 @@ struct GatherArgs {
     unsigned long long *dbg;         // DDS_DEBUG_TIMING: per CTA [entry, plan done, first data, last warp done] (globaltimer ns)
     // ---- collective owner-push fetch (FIXED only; see the protocol at dds_gather_kernel's push section)
     const ddsk_push_t *push; // device copy of the windows' table; NULL: ordinary (pull) batch
-    const int64_t *push_src_idx; // this rank's index list for the step (copied into its window by CTA 0)
-    int64_t push_nreq;           // ... and its length
+    int64_t push_nreq;           // length of this rank's index list for the step (the list is already in its window)
     unsigned long long push_step;
-    unsigned int *push_counters; // [0] warps finished
 };
 
 // the walk's granularity for segment tables: segment sizes of variable-count launches are multiples of this
@@ -1487,7 +1485,6 @@ int g_pdl = 1;
 unsigned long long *g_dbg = nullptr;
 constexpr size_t kDbgRegion = 4096 + 8;
 int g_l2_persist = 1;    // DDS_L2_PERSIST: keep per-sample tables in the persisting part of L2 (A/B switch)
-int g_plan_carveout = 1; // DDS_PLAN_CARVEOUT: plan kernels ask for the gather's shared-memory carve-out (A/B switch)
 int g_smem_plan = 1; // DDS_SMEM_PLAN: 1 = plan in shared memory when it fits (default), 0 = always the plan kernels (A/B switch)
 
 int pick_geometry() {
@@ -1508,7 +1505,6 @@ int pick_geometry() {
     if (const char *e = getenv("DDS_PDL")) g_pdl = atoi(e) != 0;
     if (const char *e = getenv("DDS_SMEM_PLAN")) g_smem_plan = atoi(e);
     if (const char *e = getenv("DDS_SMEM_PLAN_MAX")) g_plan_smem_default = atoll(e);
-    if (const char *e = getenv("DDS_PLAN_CARVEOUT")) g_plan_carveout = atoi(e);
     if (const char *e = getenv("DDS_L2_PERSIST")) g_l2_persist = atoi(e);
     if (const char *e = getenv("DDS_DEBUG_TIMING"))
         if (atoi(e)) {
@@ -1577,15 +1573,6 @@ thread_local size_t g_l2_bytes = 0;
 
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
-    // The plan kernels are meant to run on SMs that a gather CTA (max shared-memory carve-out) still occupies: ask for
-    // the same carve-out, or the SM would have to drain before it can host them.
-    static std::atomic<unsigned long long> configured{0};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (g_plan_carveout && (dev >= 64 || !(configured.load() & (1ull << dev)))) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        if (dev < 64) configured.fetch_or(1ull << dev);
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -1706,7 +1693,7 @@ int ddsk_gather_fixed(const ddsk_var_t *var, const int64_t *starts_dev, int64_t 
 
 int ddsk_gather_push(const ddsk_var_t *var, const ddsk_push_t *push_host, const ddsk_push_t *push_dev,
                      const int64_t *starts_dev, int64_t count, int64_t nreq, unsigned long long step,
-                     const ddsk_scratch_t *scr, unsigned int *push_counters, void *stream) {
+                     const ddsk_scratch_t *scr, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = pick_geometry()) return rc;
     GatherArgs a;
@@ -1724,10 +1711,8 @@ int ddsk_gather_push(const ddsk_var_t *var, const ddsk_push_t *push_host, const 
     if (nreq > 0) // this rank's list into its window, stream-ordered before the kernel that publishes it
         CUDA_TRY(cudaMemcpyAsync(push_host->win[push_host->me] + push_host->idx_off[step & 1ull], starts_dev, (size_t)nreq * 8,
                                  cudaMemcpyDeviceToDevice, st));
-    a.push_src_idx = starts_dev;
     a.push_nreq = nreq;
     a.push_step = step;
-    a.push_counters = push_counters;
     return launch_gather<true>(a, st);
 }
 

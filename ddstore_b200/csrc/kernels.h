@@ -118,10 +118,10 @@ typedef struct ddsk_push {
 } ddsk_push_t;
 /* One step of the collective fetch: publish this rank's `nreq` start rows (device array), wait for every rank's list,
  * push the rows THIS rank owns into the requesters' windows, wait until every owner's rows have landed here.
- * push_host / push_dev: the table above and its device copy; counters: 1 zeroed device word. Result: window dst buffer [step & 1]. */
+ * push_host / push_dev: the table above and its device copy. Result: window dst buffer [step & 1]. */
 int ddsk_gather_push(const ddsk_var_t *var, const ddsk_push_t *push_host, const ddsk_push_t *push_dev,
                      const int64_t *starts_dev, int64_t count, int64_t nreq, unsigned long long step,
-                     const ddsk_scratch_t *scr, unsigned int *push_counters, void *stream);
+                     const ddsk_scratch_t *scr, void *stream);
 
 /* One request in a 1-CTA kernel (the legacy per-sample get()): checks + copy into `dst` (device memory or mapped pinned
  * host memory), then flag[0] = status word, flag[1] = bytes, flag[2] = ticket (flag = mapped pinned host words). */

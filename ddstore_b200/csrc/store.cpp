@@ -258,7 +258,6 @@ struct dds_store {
         bool ready = false;
         ddsk_push_t table;
         ddsk_push_t *d_table = nullptr;
-        unsigned int *d_counters = nullptr;
         unsigned long long step = 0;
     } push;
 };
@@ -1552,8 +1551,6 @@ int dds_push_setup(dds_store_t *s, int64_t max_requests, int64_t max_bytes) {
     CU(cudaMemset(t.win[t.me] + 24, 0xFF, 8)); // the window's status word starts as "ok"
     CU(cudaMalloc((void **)&s->push.d_table, sizeof(ddsk_push_t)));
     CU(cudaMemcpy(s->push.d_table, &t, sizeof(t), cudaMemcpyHostToDevice));
-    CU(cudaMalloc((void **)&s->push.d_counters, 16));
-    CU(cudaMemset(s->push.d_counters, 0, 16));
     s->push.step = 0;
     if (int rc = dds_comm_barrier(s->comm)) return rc; // every window is armed before anyone pushes
     s->push.ready = true;
@@ -1579,7 +1576,7 @@ int dds_get_batch_push(dds_store_t *s, const char *name, const int64_t *starts_d
     }
     s->run_len = 0;
     const unsigned long long step = ++s->push.step;
-    if (ddsk_gather_push(&v->kv, &s->push.table, s->push.d_table, starts_dev, fixed_count, nreq, step, &s->scr, s->push.d_counters, st))
+    if (ddsk_gather_push(&v->kv, &s->push.table, s->push.d_table, starts_dev, fixed_count, nreq, step, &s->scr, st))
         return fail(DDS_ERR_CUDA, ddsk_last_cuda_error());
     *dst_out = s->push.table.win[s->push.table.me] + s->push.table.dst_off[step & 1ull];
     s->pending = true; // dds_batch_wait reports what the owners found wrong with this rank's requests
@@ -1659,7 +1656,6 @@ int dds_free(dds_store_t *s) {
     s->zombie_blocks.clear();
     s->multi_key.clear();
     if (s->push.d_table) cudaFree(s->push.d_table);
-    if (s->push.d_counters) cudaFree(s->push.d_counters);
     s->push = dds_store::Push();
     return rc ? rc : rc2;
 }
@@ -1714,8 +1710,7 @@ void dds_destroy(dds_store_t *s) {
         if (s->db_stream) cudaStreamDestroy(s->db_stream);
         if (s->d_multi_vars) cudaFree(s->d_multi_vars);
         if (s->push.d_table) cudaFree(s->push.d_table);
-        if (s->push.d_counters) cudaFree(s->push.d_counters);
-        if (s->stream) cudaStreamDestroy(s->stream);
+            if (s->stream) cudaStreamDestroy(s->stream);
     }
     (void)cudaGetLastError();
     delete s;
